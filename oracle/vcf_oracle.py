@@ -1,0 +1,488 @@
+"""CPU oracle for VCF's colour + block-DCT + deadzone hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``vcf_b200/`` may import this module;
+only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
+``--impl reference`` legs do, and only as the checker / the thing timed on the
+host cores -- never on the product path.
+
+PARITY STATUS: **unpinned at the arithmetic boundary.**  The reference
+(/root/reference, Sistemas-Multimedia/VCF) delegates the arithmetic of this
+path to four pip-from-git packages pinned to moving branch heads
+(requirements.txt:9-13: DCT2D@master, color_transforms@main,
+scalar_quantization@master, information_theory@main).  None is vendored, none is
+installable offline, and the reference ships no tests or golden vectors for
+them.  What *is* pinned:
+
+* the control flow and dtype chain of ``src/2D-DCT.py:268-372`` (encode_fn) and
+  ``:377-468`` (decode_fn): ``tests/test_reference_flow.py`` runs the UNMODIFIED
+  reference scripts from /root/reference/src in this container (through the
+  shadow packages in ``oracle/shims``) and compares their code-stream and
+  decoded image against ``encode_array`` / ``decode_array`` below; the vectors
+  are committed under ``tests/golden/`` by ``oracle/make_golden.py``;
+* the transform itself is the real ``scipy.fftpack.dct/idct`` (pocketfft, scipy
+  1.18.1) -- the same routine the external DCT2D package calls;
+* the 8-bit YCrCb fixed-point restatement is checked against the real
+  ``cv2.cvtColor`` (OpenCV 4.13) -- the routine ``color_transforms.YCrCb`` is
+  presumed to call (``src/YCrCb.py:59-60`` casts to uint8 before ``to_RGB``).
+
+Every function cites the reference line it follows.  [PRESUMED] marks semantics
+of the un-vendored packages.
+"""
+from __future__ import annotations
+
+import numpy as np
+import scipy.fftpack as _fp
+
+try:  # cv2 is only needed for the perceptual tables and the YCrCb cross-check
+    import cv2 as _cv2
+except Exception:  # pragma: no cover
+    _cv2 = None
+
+OFFSET = 128  # src/2D-DCT.py:107-108 (quantizer == "deadzone")
+
+# ----------------------------------------------------------------------------
+# colour transforms  (external color_transforms.YCoCg / .YCrCb)  [PRESUMED]
+# ----------------------------------------------------------------------------
+
+def ycocg_from_rgb(x: np.ndarray) -> np.ndarray:
+    """color_transforms.YCoCg.from_RGB, called at src/2D-DCT.py:298 and
+    src/YCoCg.py:38.  Output dtype follows the input (np.empty_like), so an
+    int16 input truncates the fractional parts on store (src/YCoCg.py:36-38)."""
+    R, G, B = x[..., 0], x[..., 1], x[..., 2]
+    o = np.empty_like(x)
+    o[..., 0] = R / 4 + G / 2 + B / 4
+    o[..., 1] = R / 2 - B / 2
+    o[..., 2] = -R / 4 + G / 2 - B / 4
+    return o
+
+
+def ycocg_to_rgb(x: np.ndarray) -> np.ndarray:
+    """color_transforms.YCoCg.to_RGB, called at src/2D-DCT.py:449 and
+    src/YCoCg.py:70.  Python evaluates ``Y + Co - Cg`` left to right; that
+    order is part of the fp64 bit-exactness contract of the decoder."""
+    Y, Co, Cg = x[..., 0], x[..., 1], x[..., 2]
+    o = np.empty_like(x)
+    o[..., 0] = Y + Co - Cg
+    o[..., 1] = Y + Cg
+    o[..., 2] = Y - Co - Cg
+    return o
+
+
+_YCC_SHIFT = 14
+_YCC_HALF = 1 << (_YCC_SHIFT - 1)
+
+
+def _rshift_round(v):
+    return (v + _YCC_HALF) >> _YCC_SHIFT
+
+
+def ycrcb_from_rgb_u8(rgb: np.ndarray) -> np.ndarray:
+    """color_transforms.YCrCb.from_RGB on a uint8 image (src/YCrCb.py:36):
+    OpenCV 8-bit fixed-point COLOR_RGB2YCrCb, restated in integer numpy
+    (constants verified exhaustively against cv2 4.13)."""
+    assert rgb.dtype == np.uint8
+    R = rgb[..., 0].astype(np.int32)
+    G = rgb[..., 1].astype(np.int32)
+    B = rgb[..., 2].astype(np.int32)
+    Y = _rshift_round(4899 * R + 9617 * G + 1868 * B)
+    Cr = _rshift_round((R - Y) * 11682 + (128 << _YCC_SHIFT))
+    Cb = _rshift_round((B - Y) * 9241 + (128 << _YCC_SHIFT))
+    out = np.stack([Y, Cr, Cb], axis=-1)
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
+def ycrcb_to_rgb_u8(ycc: np.ndarray) -> np.ndarray:
+    """color_transforms.YCrCb.to_RGB on a uint8 image (src/YCrCb.py:59-60):
+    OpenCV 8-bit fixed-point COLOR_YCrCb2RGB."""
+    assert ycc.dtype == np.uint8
+    Y = ycc[..., 0].astype(np.int32)
+    Cr = ycc[..., 1].astype(np.int32) - 128
+    Cb = ycc[..., 2].astype(np.int32) - 128
+    R = Y + _rshift_round(Cr * 22987)
+    G = Y + _rshift_round(Cb * -5636 + Cr * -11698)
+    B = Y + _rshift_round(Cb * 29049)
+    out = np.stack([R, G, B], axis=-1)
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
+# Float YCrCb in front of the DCT is an EXTENSION: the reference never reaches
+# it (src/2D-DCT.py:22-23 hard-imports the YCoCg functions; -t only selects the
+# base class, :54-56).  BASELINE.json config 5 ("YCrCb + B=16") needs a
+# definition, so it is fixed here: the BT.601 analog matrix OpenCV uses for
+# floating-point images, with every product and sum a separately rounded
+# operation in the working dtype, evaluated left to right, and no chroma delta
+# (the input is already centred by the -128 shift).
+YCC_KR, YCC_KG, YCC_KB = 0.299, 0.587, 0.114
+YCC_CR, YCC_CB = 0.713, 0.564
+YCC_R_CR, YCC_G_CR, YCC_G_CB, YCC_B_CB = 1.403, -0.714, -0.344, 1.773
+
+
+def ycrcb_from_rgb_float(x: np.ndarray) -> np.ndarray:
+    """Extension (see above).  x is a centred float image."""
+    dt = x.dtype.type
+    R, G, B = x[..., 0], x[..., 1], x[..., 2]
+    o = np.empty_like(x)
+    Y = (R * dt(YCC_KR) + G * dt(YCC_KG)) + B * dt(YCC_KB)
+    o[..., 0] = Y
+    o[..., 1] = (R - Y) * dt(YCC_CR)
+    o[..., 2] = (B - Y) * dt(YCC_CB)
+    return o
+
+
+def ycrcb_to_rgb_float(x: np.ndarray) -> np.ndarray:
+    """Extension (see above): inverse of ycrcb_from_rgb_float."""
+    dt = x.dtype.type
+    Y, Cr, Cb = x[..., 0], x[..., 1], x[..., 2]
+    o = np.empty_like(x)
+    o[..., 0] = Y + Cr * dt(YCC_R_CR)
+    o[..., 1] = (Y + Cr * dt(YCC_G_CR)) + Cb * dt(YCC_G_CB)
+    o[..., 2] = Y + Cb * dt(YCC_B_CB)
+    return o
+
+
+# ----------------------------------------------------------------------------
+# block DCT  (external DCT2D.block_DCT)  [PRESUMED]
+# ----------------------------------------------------------------------------
+
+def analyze_block(block: np.ndarray) -> np.ndarray:
+    """2-D orthonormal DCT-II of one (B,B,C) block: axis 0 first, then axis 1.
+    In-repo corroboration: src/IPP_DCT.py:257-259
+    ``dct(dct(block.T, norm='ortho').T, norm='ortho')`` (same order for 2-D)."""
+    return _fp.dct(_fp.dct(block, norm="ortho", axis=0), norm="ortho", axis=1)
+
+
+def synthesize_block(block: np.ndarray) -> np.ndarray:
+    """Inverse of analyze_block (src/IPP_DCT.py:261-263): axis 0, then axis 1."""
+    return _fp.idct(_fp.idct(block, norm="ortho", axis=0), norm="ortho", axis=1)
+
+
+def analyze_image_loop(img: np.ndarray, by: int, bx: int) -> np.ndarray:
+    """DCT2D.block_DCT.analyze_image as the reference executes it: a Python
+    loop over blocks, two scipy calls per block (src/2D-DCT.py:303).  scipy
+    keeps float32 for float32 input and promotes integers to float64."""
+    ny, nx = img.shape[0] // by, img.shape[1] // bx
+    out_dtype = np.result_type(img.dtype, np.float32) if img.dtype.kind == "f" else np.float64
+    out = np.empty(img.shape, dtype=out_dtype)
+    for y in range(ny):
+        for x in range(nx):
+            blk = img[y * by:(y + 1) * by, x * bx:(x + 1) * bx]
+            out[y * by:(y + 1) * by, x * bx:(x + 1) * bx] = analyze_block(blk)
+    return out
+
+
+def synthesize_image_loop(coef: np.ndarray, by: int, bx: int) -> np.ndarray:
+    """DCT2D.block_DCT.synthesize_image, loop form (src/2D-DCT.py:440)."""
+    ny, nx = coef.shape[0] // by, coef.shape[1] // bx
+    out_dtype = np.result_type(coef.dtype, np.float32) if coef.dtype.kind == "f" else np.float64
+    out = np.empty(coef.shape, dtype=out_dtype)
+    for y in range(ny):
+        for x in range(nx):
+            blk = coef[y * by:(y + 1) * by, x * bx:(x + 1) * bx]
+            out[y * by:(y + 1) * by, x * bx:(x + 1) * bx] = synthesize_block(blk)
+    return out
+
+
+def analyze_image(img: np.ndarray, by: int, bx: int) -> np.ndarray:
+    """Vectorised form of analyze_image_loop: one scipy call per axis over all
+    blocks.  Bit-identical to the loop (tests/test_oracle.py) because pocketfft
+    applies the same 1-D kernel to every line."""
+    H, W, C = img.shape
+    b = img.reshape(H // by, by, W // bx, bx, C)
+    b = _fp.dct(_fp.dct(b, norm="ortho", axis=1), norm="ortho", axis=3)
+    return b.reshape(H, W, C)
+
+
+def synthesize_image(coef: np.ndarray, by: int, bx: int) -> np.ndarray:
+    """Vectorised form of synthesize_image_loop."""
+    H, W, C = coef.shape
+    b = coef.reshape(H // by, by, W // bx, bx, C)
+    b = _fp.idct(_fp.idct(b, norm="ortho", axis=1), norm="ortho", axis=3)
+    return b.reshape(H, W, C)
+
+
+def get_subbands(coef: np.ndarray, by: int, bx: int) -> np.ndarray:
+    """DCT2D.block_DCT.get_subbands (src/2D-DCT.py:336):
+    sub[j*ny + y, i*nx + x, c] = coef[y*by + j, x*bx + i, c].
+    Block convention corroborated by src/2D-KLT.py:571,583."""
+    H, W, C = coef.shape
+    return np.ascontiguousarray(
+        coef.reshape(H // by, by, W // bx, bx, C).transpose(1, 0, 3, 2, 4)
+    ).reshape(H, W, C)
+
+
+def get_blocks(sub: np.ndarray, by: int, bx: int) -> np.ndarray:
+    """DCT2D.block_DCT.get_blocks (src/2D-DCT.py:416): inverse permutation."""
+    H, W, C = sub.shape
+    return np.ascontiguousarray(
+        sub.reshape(by, H // by, bx, W // bx, C).transpose(1, 0, 3, 2, 4)
+    ).reshape(H, W, C)
+
+
+# ----------------------------------------------------------------------------
+# deadzone quantizer  (external scalar_quantization.deadzone_quantization)
+# ----------------------------------------------------------------------------
+
+class DeadzoneQuantizer:
+    """Deadzone_Quantizer(Q_step, min_val, max_val) built at src/deadzone.py:64.
+    [PRESUMED] encode = truncation toward zero of x / Q_step (dead zone
+    (-q, q)); decode = Q_step * k, no mid-point reconstruction.  min_val and
+    max_val are accepted and unused.  The result must be an integer array that
+    accepts ``k += 128`` in place (src/2D-DCT.py:348)."""
+
+    name = "deadzone"
+
+    def __init__(self, Q_step, min_val=0, max_val=255):
+        self.Q_step = Q_step
+        self.min_val = min_val
+        self.max_val = max_val
+
+    def encode(self, x):
+        return (x / self.Q_step).astype(np.int64)
+
+    def decode(self, k):
+        return self.Q_step * k
+
+
+# ----------------------------------------------------------------------------
+# padding (src/2D-DCT.py:187-229, :231-266)
+# ----------------------------------------------------------------------------
+
+def padded_shape(H: int, W: int, B: int):
+    """Target dims and (top, left) offsets of src/2D-DCT.py:208-219."""
+    Hp = (H + B - 1) // B * B
+    Wp = (W + B - 1) // B * B
+    return Hp, Wp, (Hp - H) // 2, (Wp - W) // 2
+
+
+def pad_and_center(img: np.ndarray, B: int) -> np.ndarray:
+    """src/2D-DCT.py:187-229: zero padding, centred, remainder bottom/right."""
+    H, W, _ = img.shape
+    Hp, Wp, top, left = padded_shape(H, W, B)
+    return np.pad(img, ((top, Hp - H - top), (left, Wp - W - left), (0, 0)),
+                  mode="constant", constant_values=0)
+
+
+def remove_padding(img: np.ndarray, shape) -> np.ndarray:
+    """src/2D-DCT.py:231-266."""
+    H, W = shape[0], shape[1]
+    top = (img.shape[0] - H) // 2
+    left = (img.shape[1] - W) // 2
+    return img[top:top + H, left:left + W, :]
+
+
+# ----------------------------------------------------------------------------
+# perceptual weights (src/2D-DCT.py:63-90)
+# ----------------------------------------------------------------------------
+
+_Y_QSS = np.array([[16, 11, 10, 16, 24, 40, 51, 61],
+                   [12, 12, 14, 19, 26, 58, 60, 55],
+                   [14, 13, 16, 24, 40, 57, 69, 56],
+                   [14, 17, 22, 29, 51, 87, 80, 62],
+                   [18, 22, 37, 56, 68, 109, 103, 77],
+                   [24, 35, 55, 64, 81, 104, 113, 92],
+                   [49, 64, 78, 87, 103, 121, 120, 101],
+                   [72, 92, 95, 98, 112, 100, 103, 99]])
+_C_QSS = np.array([[17, 18, 24, 47, 99, 99, 99, 99],
+                   [18, 21, 26, 66, 99, 99, 99, 99],
+                   [24, 26, 56, 99, 99, 99, 99, 99],
+                   [47, 66, 99, 99, 99, 99, 99, 99],
+                   [99, 99, 99, 99, 99, 99, 99, 99],
+                   [99, 99, 99, 99, 99, 99, 99, 99],
+                   [99, 99, 99, 99, 99, 99, 99, 99],
+                   [99, 99, 99, 99, 99, 99, 99, 99]])
+
+
+def perceptual_tables(B: int):
+    """(Y_QSSs, C_QSSs) as built at src/2D-DCT.py:66-90: JPEG tables as uint8,
+    cv2.resize to BxB (INTER_AREA below 8, INTER_LINEAR otherwise)."""
+    inter = _cv2.INTER_AREA if B < 8 else _cv2.INTER_LINEAR
+    C = _cv2.resize(_C_QSS.astype(np.uint8), (B, B), interpolation=inter)
+    Y = _cv2.resize(_Y_QSS.astype(np.uint8), (B, B), interpolation=inter)
+    return Y, C
+
+
+# ----------------------------------------------------------------------------
+# the path: src/2D-DCT.py:268-372 (encode_fn) and :377-468 (decode_fn),
+# without the file IO and entropy coding on either side.
+# ----------------------------------------------------------------------------
+
+def encode_array(img_u8: np.ndarray, B: int = 8, q=32, *, color: str = "YCoCg",
+                 dtype=np.float32, perceptual: bool = False,
+                 disable_subbands: bool = False, loop: bool = False) -> np.ndarray:
+    """uint8 RGB (H,W,3) -> uint8 indices (Hp,Wp,3), the array handed to
+    ``self.compress`` at src/2D-DCT.py:364.
+
+    dtype=np.float32 is the reference's own precision (:276); np.float64 is
+    the validation mode.  color="YCrCb" selects the float extension defined
+    above (NOT a reference behaviour: with ``-t YCrCb`` the reference still
+    runs the YCoCg arithmetic, :22-23)."""
+    img = img_u8.astype(dtype)                                   # :276
+    img = pad_and_center(img, B)                                 # :282
+    img -= OFFSET                                                # :292
+    if color == "YCoCg":
+        ct = ycocg_from_rgb(img)                                 # :298
+    elif color == "YCrCb":
+        ct = ycrcb_from_rgb_float(img)
+    else:
+        raise ValueError(color)
+    coef = (analyze_image_loop if loop else analyze_image)(ct, B, B)   # :303
+    if perceptual:                                               # :313-327
+        Yq, Cq = perceptual_tables(B)
+        ny, nx = coef.shape[0] // B, coef.shape[1] // B
+        blk = coef.reshape(ny, B, nx, B, 3)
+        # ``block[..., 0] *= (Y_QSSs/121)``: float64 factor, in-place on the
+        # coefficient dtype (numpy casts the product back, same_kind).
+        blk[..., 0] *= (Yq / 121)[None, :, None, :]
+        blk[..., 1] *= (Cq / 99)[None, :, None, :]
+        blk[..., 2] *= (Cq / 99)[None, :, None, :]
+    decom = coef if disable_subbands else get_subbands(coef, B, B)  # :333-336
+    k = DeadzoneQuantizer(q).encode(decom)                       # :343
+    k += OFFSET                                                  # :348
+    return k.astype(np.uint8)                                    # :361 (wraps)
+
+
+def decode_array(idx_u8: np.ndarray, shape, B: int = 8, q=32, *, color: str = "YCoCg",
+                 perceptual: bool = False, disable_subbands: bool = False,
+                 loop: bool = False, return_float: bool = False,
+                 dtype=None) -> np.ndarray:
+    """uint8 indices (Hp,Wp,3) -> uint8 RGB (H,W,3) written at :467.
+
+    The reference's dtype chain (dtype=None): int16 indices (:398), int16
+    dequantised values (numpy keeps int16 * python-int), float64 IDCT (scipy
+    promotes integers), float64 colour transform, truncation to uint8 (:466).
+    dtype=np.float32 restates the same flow with a float32 IDCT (the fast
+    mode of the GPU decoder is compared against the float64 chain, not this).
+    return_float hands back the un-clipped float image that
+    ``CT.CoDec.filter`` receives (:461)."""
+    k = idx_u8.astype(np.int16)                                  # :398
+    k -= OFFSET                                                  # :402
+    y = DeadzoneQuantizer(q).decode(k)                           # :410
+    if dtype is not None:
+        y = y.astype(dtype)
+    coef = y if disable_subbands else get_blocks(y, B, B)        # :413-416
+    if perceptual:                                               # :421-435
+        Yq, Cq = perceptual_tables(B)
+        ny, nx = coef.shape[0] // B, coef.shape[1] // B
+        blk = coef.reshape(ny, B, nx, B, 3)
+        f = blk.astype(np.float32)
+        f[..., 0] /= (Yq / 121)[None, :, None, :]
+        f[..., 1] /= (Cq / 99)[None, :, None, :]
+        f[..., 2] /= (Cq / 99)[None, :, None, :]
+        blk[...] = f          # stored back into the (int16) array: truncates
+    ct = (synthesize_image_loop if loop else synthesize_image)(coef, B, B)  # :440
+    ct = remove_padding(ct, shape)                               # :444
+    if color == "YCoCg":
+        y = ycocg_to_rgb(ct)                                     # :449
+    elif color == "YCrCb":
+        y = ycrcb_to_rgb_float(ct)
+    else:
+        raise ValueError(color)
+    y += OFFSET                                                  # :454
+    if return_float:
+        return y
+    return np.clip(y, 0, 255).astype(np.uint8)                   # :466 (truncation)
+
+
+# ----------------------------------------------------------------------------
+# stand-alone colour codecs (src/YCoCg.py:33-85, src/YCrCb.py:33-69)
+# ----------------------------------------------------------------------------
+
+def ycocg_standalone_encode(img_u8: np.ndarray, q=32) -> np.ndarray:
+    """src/YCoCg.py:33-55 with the deadzone quantizer (offset 0, :28-29)."""
+    img = img_u8.astype(np.int16)                                # :36
+    ycc = ycocg_from_rgb(img)                                    # :38 (int16 store truncates)
+    k = DeadzoneQuantizer(q).encode(ycc)                         # :44
+    return k.astype(np.uint16)                                   # :52
+
+
+def ycocg_standalone_decode(k_u16: np.ndarray, q=32) -> np.ndarray:
+    """src/YCoCg.py:57-85."""
+    k = k_u16.astype(np.int16)                                   # :61
+    y = DeadzoneQuantizer(q).decode(k)                           # :64
+    rgb = ycocg_to_rgb(y)                                        # :70
+    return np.clip(rgb, 0, 255).astype(np.uint8)                 # :78
+
+
+def ycrcb_standalone_encode(img_u8: np.ndarray, q=32) -> np.ndarray:
+    """src/YCrCb.py:33-50."""
+    ycc = ycrcb_from_rgb_u8(img_u8).astype(np.int16)             # :36
+    k = DeadzoneQuantizer(q).encode(ycc)                         # :41
+    return k.astype(np.uint16)                                   # :47
+
+
+def ycrcb_standalone_decode(k_u16: np.ndarray, q=32) -> np.ndarray:
+    """src/YCrCb.py:52-69 (note the uint8 cast before to_RGB, :59)."""
+    y = DeadzoneQuantizer(q).decode(k_u16).astype(np.int16)      # :56
+    y = y.astype(np.uint8)                                       # :59 (wraps)
+    rgb = ycrcb_to_rgb_u8(y)                                     # :60
+    return np.clip(rgb, 0, 255).astype(np.uint8)                 # :66
+
+
+# ----------------------------------------------------------------------------
+# rate/distortion statistics (src/RDE.py:12-55, src/2D-DCT.py:574)
+# ----------------------------------------------------------------------------
+
+def rmse(a: np.ndarray, b: np.ndarray):
+    """src/RDE.py:30-53: both images to float32, mean of squared differences
+    over all H*W*3 samples, square root.  Also information_theory.
+    distortion.RMSE [PRESUMED] (src/2D-DCT.py:574)."""
+    d = a.astype(np.float32) - b.astype(np.float32)
+    return np.sqrt((d ** 2).mean())
+
+
+def sse_int(a_u8: np.ndarray, b_u8: np.ndarray) -> int:
+    """Exact integer sum of squared errors (what the GPU statistic kernel
+    accumulates); RMSE = sqrt(SSE / N) up to float32 rounding of the mean."""
+    d = a_u8.astype(np.int64) - b_u8.astype(np.int64)
+    return int((d * d).sum())
+
+
+def psnr(a_u8: np.ndarray, b_u8: np.ndarray) -> float:
+    n = a_u8.size
+    s = sse_int(a_u8, b_u8)
+    if s == 0:
+        return float("inf")
+    return float(10.0 * np.log10(255.0 * 255.0 * n / s))
+
+
+def index_stats(idx_u8: np.ndarray):
+    """Zero-order statistics of the code-stream payload: non-zero count,
+    sum |k| (k = signed index, wrapped like int8 around the 128 bias) and the
+    256-bin histogram per channel the entropy estimate is computed from."""
+    k = (idx_u8.astype(np.int16) - 128)
+    nz = int((k != 0).sum())
+    sabs = int(np.abs(k).sum())
+    hist = np.stack([np.bincount(idx_u8[..., c].ravel(), minlength=256) for c in range(3)])
+    return nz, sabs, hist.astype(np.int64)
+
+
+def entropy_bits(hist: np.ndarray) -> float:
+    """Zero-order entropy (bits) of a 256-bin histogram."""
+    h = hist.astype(np.float64)
+    n = h.sum()
+    if n == 0:
+        return 0.0
+    p = h[h > 0] / n
+    return float(-(p * np.log2(p)).sum() * n)
+
+
+# ----------------------------------------------------------------------------
+# synthetic inputs
+# ----------------------------------------------------------------------------
+
+def synthetic_frame(H: int, W: int, seed: int, kind: str = "natural") -> np.ndarray:
+    """Seeded synthetic uint8 RGB frame.  kind="noise": i.i.d. uniform[0,255];
+    kind="natural": smooth sinusoid field + N(0,6) noise, clipped."""
+    rng = np.random.default_rng(seed)
+    if kind == "noise":
+        return rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    ph = rng.uniform(0, 2 * np.pi, size=(3, 3)).astype(np.float32)
+    fr = rng.uniform(0.5, 3.0, size=(3, 2)).astype(np.float32)
+    img = np.empty((H, W, 3), dtype=np.float32)
+    for c in range(3):
+        img[..., c] = (128 + 70 * np.sin(2 * np.pi * fr[c, 0] * xx / W + ph[c, 0])
+                       * np.cos(2 * np.pi * fr[c, 1] * yy / H + ph[c, 1])
+                       + 30 * np.sin(2 * np.pi * (xx + yy) / 97.0 + ph[c, 2]))
+    img += rng.normal(0, 6, size=img.shape).astype(np.float32)
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
