@@ -1,0 +1,27 @@
+# libvcfb200.so -- sm_100a only.  `make` builds in-tree (vcf_b200/libvcfb200.so) so the
+# shared object travels with the repo snapshot to the GPU box.
+NVCC      ?= nvcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVCCFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Iinclude -Ivcf_b200/csrc
+SRCS      := vcf_b200/csrc/api.cu vcf_b200/csrc/kernels_general.cu vcf_b200/csrc/kernels_fast.cu
+SRCS      := $(wildcard $(SRCS))
+OBJS      := $(patsubst vcf_b200/csrc/%.cu,build/%.o,$(SRCS))
+HDRS      := $(wildcard vcf_b200/csrc/*.cuh) include/vcfb200.h
+LIB       := vcf_b200/libvcfb200.so
+
+all: $(LIB)
+
+build/%.o: vcf_b200/csrc/%.cu $(HDRS)
+	@mkdir -p build
+	$(NVCC) $(NVCCFLAGS) -Xptxas -v -c $< -o $@ 2> build/$*.ptxas.log || (cat build/$*.ptxas.log; exit 1)
+
+$(LIB): $(OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS)
+
+codelets:
+	python vcf_b200/codegen/gen_cuda.py
+
+clean:
+	rm -rf build $(LIB)
+
+.PHONY: all clean codelets

@@ -1,0 +1,134 @@
+/* libvcfb200 -- C ABI of the B200-native colour + block-DCT + deadzone path of
+ * the Visual Coding Framework (Sistemas-Multimedia/VCF).
+ *
+ * This is the drop-in boundary.  The reference has no FFI of its own (it is pure
+ * Python); the entry points below are what a ctypes binding inside the
+ * reference's spatial-transform stage binds in place of the numpy/scipy
+ * arithmetic.  Each one names the reference code it replaces (paths relative
+ * to the reference repository).  INTEGRATION.md shows the binding.
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; every function returns 0 on success or a
+ *     negative VCFB_E_* code and never throws; vcfb_last_error() gives the text
+ *     of the last failure on the calling thread;
+ *   - images are interleaved 8-bit RGB, shape (n_frames, H, W, 3), C order;
+ *     index arrays are uint8, shape (n_frames, Hp, Wp, 3) with Hp, Wp = H, W
+ *     rounded up to a multiple of B (vcfb_padded_dims);
+ *   - the *_dev entry points take DEVICE pointers and a CUDA stream (0 = legacy
+ *     default stream; pass torch's current stream handle from Python), are
+ *     asynchronous, re-entrant per stream and keep no global mutable state;
+ *   - the host entry points take HOST pointers, stage through pinned memory
+ *     owned by an explicit context and return when the result is in the output
+ *     buffer;
+ *   - the caller owns every buffer.
+ *   - There is no CPU fallback: without a CUDA device every compute entry point
+ *     fails with VCFB_E_CUDA.
+ */
+#ifndef VCFB200_H
+#define VCFB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VCFB_VERSION 100 /* 0.1.0 */
+
+/* error codes */
+#define VCFB_OK 0
+#define VCFB_E_ARG (-1)     /* bad argument (NULL pointer, unsupported B, q <= 0, ...) */
+#define VCFB_E_CUDA (-2)    /* CUDA runtime error (text in vcfb_last_error) */
+#define VCFB_E_UNSUPP (-3)  /* valid request this build does not implement */
+
+/* colour transform applied in front of the DCT */
+#define VCFB_COLOR_YCOCG 0 /* color_transforms.YCoCg.from_RGB/to_RGB, the only one
+                              src/2D-DCT.py reaches (:22-23, :298, :449) */
+#define VCFB_COLOR_YCRCB 1 /* float BT.601 extension defined by oracle/vcf_oracle.py
+                              (BASELINE.json config 5); not a reference behaviour */
+
+/* flags */
+#define VCFB_F_NO_SUBBANDS 1u /* -x / --disable_subbands (src/2D-DCT.py:40, :333, :413) */
+#define VCFB_F_PERCEPTUAL 2u  /* -p / --perceptual_quantization (:38, :313-327, :421-435);
+                                 needs `weights` */
+#define VCFB_F_FP64 4u        /* encode: validation mode, float64 arithmetic (indices
+                                 bit-exact with the oracle evaluated in float64);
+                                 decode: the reference's own float64 chain
+                                 (:398-466), pixels bit-exact */
+#define VCFB_F_CONTRACT 8u    /* float32 only: let the compiler fuse multiply-adds in
+                                 the DCT.  Without it the float32 encoder is bit-exact
+                                 with the reference's float32 path (:276); with it
+                                 < 1e-6 of the indices may differ. */
+
+/* statistics vector (int64), accumulated with integer atomics; the caller zeroes it.
+ * Integer sums make the multi-GPU all-reduce order-independent. */
+#define VCFB_STAT_SSE_R 0      /* sum (original - decoded)^2, channel R  (src/RDE.py:41-49) */
+#define VCFB_STAT_SSE_G 1
+#define VCFB_STAT_SSE_B 2
+#define VCFB_STAT_NSAMPLES 3   /* samples compared (H*W*3 per frame) */
+#define VCFB_STAT_NONZERO 4    /* indices != 0 after removing the 128 bias */
+#define VCFB_STAT_SUMABS 5     /* sum |index| */
+#define VCFB_STAT_NINDICES 6   /* indices written (Hp*Wp*3 per frame) */
+#define VCFB_STAT_RESERVED 7
+#define VCFB_STAT_HIST 8       /* 3 x 256 histogram of the uint8 indices, channel-major */
+#define VCFB_STAT_LEN (8 + 3 * 256)
+
+int vcfb_version(void);
+const char* vcfb_last_error(void);
+
+/* Number of CUDA devices visible (0 if none / no driver). */
+int vcfb_device_count(void);
+
+/* src/2D-DCT.py:208-219 (pad_and_center_to_multiple_of_block_size): padded dims
+ * and the top/left offsets of the centred image. */
+int vcfb_padded_dims(int H, int W, int B, int* Hp, int* Wp, int* top, int* left);
+
+/* Encode: replaces src/2D-DCT.py:276-361 between encode_read_fn and compress --
+ *   astype(float32) :276, pad :282, -=128 :292, from_RGB :298, space_analyze :303,
+ *   perceptual scale :313-327, get_subbands :336, quantize_decom :343
+ *   (src/deadzone.py:95-105), += 128 :348, astype(uint8) :361 (wraps, no clip).
+ * rgb      (n_frames,H,W,3) uint8, device
+ * q        quantisation step (-q / QSS, src/deadzone.py:30), > 0
+ * weights  2*B*B doubles, device: Y_QSSs/121 then C_QSSs/99 (src/2D-DCT.py:322-324),
+ *          row-major [j][i]; NULL unless VCFB_F_PERCEPTUAL
+ * idx_out  (n_frames,Hp,Wp,3) uint8, device
+ * stats    VCFB_STAT_LEN int64 on the device or NULL; adds NONZERO, SUMABS,
+ *          NINDICES and HIST */
+int vcfb_encode_dev(const uint8_t* rgb, int n_frames, int H, int W, int B, double q,
+                    int color, unsigned flags, const double* weights,
+                    uint8_t* idx_out, int64_t* stats, void* cuda_stream);
+
+/* Decode: replaces src/2D-DCT.py:398-466 between decompress and decode_write_fn --
+ *   astype(int16) :398, -=128 :402, dequantize_decom :410 (src/deadzone.py:107-120),
+ *   get_blocks :416, perceptual :421-435, space_synthesize :440, remove_padding :444,
+ *   to_RGB :449, += 128 :454, [filter hook :461], clip + astype(uint8) :466.
+ * idx        (n_frames,Hp,Wp,3) uint8, device
+ * rgb_out    (n_frames,H,W,3) uint8, device, or NULL
+ * y_out      (n_frames,H,W,3) un-clipped image handed to CT.CoDec.filter (:461):
+ *            float64 with VCFB_F_FP64, float32 otherwise; device, or NULL
+ * original   (n_frames,H,W,3) uint8, device, or NULL; with `stats` adds the SSE
+ *            between it and the clipped uint8 result (src/RDE.py:12-55) */
+int vcfb_decode_dev(const uint8_t* idx, int n_frames, int H, int W, int B, double q,
+                    int color, unsigned flags, const double* weights,
+                    uint8_t* rgb_out, void* y_out, const uint8_t* original,
+                    int64_t* stats, void* cuda_stream);
+
+/* Host-buffer convenience layer (what a numpy caller binds).  A context owns one
+ * CUDA stream plus pinned and device staging buffers that grow on demand. */
+typedef struct vcfb_ctx vcfb_ctx;
+int vcfb_ctx_create(int device, vcfb_ctx** out);
+void vcfb_ctx_destroy(vcfb_ctx* ctx);
+
+/* Same contracts as the *_dev calls with HOST pointers (weights, stats too);
+ * stats (may be NULL) receives this call's statistics (overwritten, not added). */
+int vcfb_encode_host(vcfb_ctx* ctx, const uint8_t* rgb, int n_frames, int H, int W, int B,
+                     double q, int color, unsigned flags, const double* weights,
+                     uint8_t* idx_out, int64_t* stats);
+int vcfb_decode_host(vcfb_ctx* ctx, const uint8_t* idx, int n_frames, int H, int W, int B,
+                     double q, int color, unsigned flags, const double* weights,
+                     uint8_t* rgb_out, void* y_out, const uint8_t* original, int64_t* stats);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VCFB200_H */

@@ -1,0 +1,235 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle and the
+golden vectors recorded from the unmodified reference.  Needs a B200."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import vcf_oracle as O
+from _util import parse_flags as _parse
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def _codec(**kw):
+    from vcf_b200 import Codec
+    return Codec(**kw)
+
+
+# ---------------------------------------------------------------------------
+# golden vectors of the reference (bit-exact, float32 encode / float64 decode)
+# ---------------------------------------------------------------------------
+FILES = sorted(f for f in glob.glob(os.path.join(GOLD, "ref_flow_*.npz")) if "sa_" not in f)
+
+
+@pytest.mark.parametrize("fn", FILES, ids=[os.path.basename(f)[9:-4] for f in FILES])
+def test_reference_golden_bit_exact(fn, torch_cuda):
+    g = np.load(fn)
+    kw = _parse(g["flags"])
+    c32 = _codec(block_size=kw["B"], q=kw["q"], perceptual=kw["perceptual"],
+                 disable_subbands=kw["disable_subbands"])
+    idx = c32.encode(g["img"])
+    assert idx.dtype == np.uint8 and idx.shape == g["idx"].shape
+    assert np.array_equal(idx, g["idx"])               # reference's own float32 path
+    c64 = _codec(block_size=kw["B"], q=kw["q"], perceptual=kw["perceptual"],
+                 disable_subbands=kw["disable_subbands"], fp64=True)
+    dec = c64.decode(g["idx"], g["img"].shape)
+    assert np.array_equal(dec, g["decoded"])           # reference's float64 decode chain
+    # same through the torch / device-pointer entry points
+    t = torch_cuda
+    idx_t = c32.encode(t.from_numpy(g["img"]).cuda())
+    assert np.array_equal(idx_t.cpu().numpy(), g["idx"])
+    dec_t = c64.decode(t.from_numpy(g["idx"]).cuda(), g["img"].shape)
+    assert np.array_equal(dec_t.cpu().numpy(), g["decoded"])
+
+
+# ---------------------------------------------------------------------------
+# seeded inputs vs the oracle
+# ---------------------------------------------------------------------------
+SHAPES = [(64, 96), (67, 91), (8, 8), (5, 3), (1, 1), (300, 520), (33, 1000)]
+
+
+@pytest.mark.parametrize("B", [4, 8, 16, 32])
+@pytest.mark.parametrize("q", [1, 5, 8, 12, 32, 64])
+def test_encode_exact_fp32_fp64(B, q, torch_cuda):
+    for si, (H, W) in enumerate(SHAPES):
+        for kind in ("noise", "natural"):
+            img = O.synthetic_frame(H, W, 100 + si, kind)
+            for fp64, dt in ((False, np.float32), (True, np.float64)):
+                ref = O.encode_array(img, B, q, dtype=dt)
+                got = _codec(block_size=B, q=q, fp64=fp64).encode(img)
+                assert got.shape == ref.shape
+                nbad = int((got != ref).sum())
+                assert nbad == 0, (B, q, H, W, kind, fp64, nbad)
+
+
+@pytest.mark.parametrize("B", [4, 8, 16, 32])
+@pytest.mark.parametrize("q", [1, 8, 12, 32])
+def test_decode_fp64_bit_exact_and_fp32_within_1lsb(B, q, torch_cuda):
+    for si, (H, W) in enumerate(SHAPES):
+        img = O.synthetic_frame(H, W, 200 + si, "natural")
+        idx = O.encode_array(img, B, q)
+        ref = O.decode_array(idx, img.shape, B, q)
+        got64 = _codec(block_size=B, q=q, fp64=True).decode(idx, img.shape)
+        assert np.array_equal(got64, ref), (B, q, H, W)
+        got32 = _codec(block_size=B, q=q).decode(idx, img.shape)
+        d = np.abs(got32.astype(np.int16) - ref.astype(np.int16))
+        assert d.max() <= 1, (B, q, H, W, int(d.max()))
+        if H * W >= 4096:
+            assert abs(O.psnr(img, got32) - O.psnr(img, ref)) < 0.01
+
+
+def test_random_indices_decode_fp64(torch_cuda):
+    """Arbitrary index arrays (not produced by an encoder), incl. the int16 wrap
+    of q*k and saturating clips."""
+    rng = np.random.default_rng(7)
+    for B in (4, 8, 16, 32):
+        for q in (3, 32, 300):
+            H, W = 64, 96
+            idx = rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+            ref = O.decode_array(idx, (H, W, 3), B, q)
+            got = _codec(block_size=B, q=q, fp64=True).decode(idx, (H, W))
+            assert np.array_equal(got, ref), (B, q)
+
+
+@pytest.mark.parametrize("B", [4, 8, 16, 32])
+def test_flags_nosub_perceptual(B, torch_cuda):
+    img = O.synthetic_frame(72, 104, 300 + B, "natural")
+    for kw in (dict(disable_subbands=True), dict(perceptual=True), dict(perceptual=True, disable_subbands=True)):
+        for q in (4, 32):
+            for fp64, dt in ((False, np.float32), (True, np.float64)):
+                ref = O.encode_array(img, B, q, dtype=dt, **kw)
+                got = _codec(block_size=B, q=q, fp64=fp64, **kw).encode(img)
+                assert np.array_equal(got, ref), (B, q, kw, fp64)
+            idx = O.encode_array(img, B, q, **kw)
+            ref = O.decode_array(idx, img.shape, B, q, **kw)
+            got = _codec(block_size=B, q=q, fp64=True, **kw).decode(idx, img.shape)
+            assert np.array_equal(got, ref), (B, q, kw)
+
+
+@pytest.mark.parametrize("B", [8, 16])
+def test_ycrcb_extension(B, torch_cuda):
+    img = O.synthetic_frame(80, 112, 400 + B, "natural")
+    for q in (8, 32):
+        for fp64, dt in ((False, np.float32), (True, np.float64)):
+            ref = O.encode_array(img, B, q, dtype=dt, color="YCrCb")
+            got = _codec(block_size=B, q=q, fp64=fp64, color="YCrCb").encode(img)
+            assert np.array_equal(got, ref), (B, q, fp64)
+        idx = O.encode_array(img, B, q, color="YCrCb")
+        ref = O.decode_array(idx, img.shape, B, q, color="YCrCb")
+        got = _codec(block_size=B, q=q, fp64=True, color="YCrCb").decode(idx, img.shape)
+        assert np.array_equal(got, ref), (B, q)
+
+
+def test_contract_mode_mismatch_rate(torch_cuda):
+    """VCFB_F_CONTRACT (fused multiply-adds allowed): < 1e-6 of the indices may
+    differ from the reference's float32 path, none at the rational positions
+    {0,B/2}^2, and only by one step."""
+    H, W = 1080, 1920
+    for kind in ("noise", "natural"):
+        img = O.synthetic_frame(H, W, 500, kind)
+        for B, q in ((8, 8), (8, 32), (16, 8)):
+            ref = O.encode_array(img, B, q)
+            got = _codec(block_size=B, q=q, contract=True).encode(img)
+            bad = np.argwhere(got != ref)
+            assert len(bad) <= max(1, int(1e-6 * ref.size)) + 2, (kind, B, q, len(bad))
+            ny, nx = H // B if H % B == 0 else (H + B - 1) // B, W // B
+            for (y, x, c) in bad:
+                j, i = y // ny, x // nx
+                assert not (j in (0, B // 2) and i in (0, B // 2))
+                assert abs(int(got[y, x, c]) - int(ref[y, x, c])) in (1, 255)
+
+
+def test_float_output_and_stats(torch_cuda):
+    img = O.synthetic_frame(120, 200, 600, "natural")
+    B, q = 8, 16
+    idx = O.encode_array(img, B, q)
+    c64 = _codec(block_size=B, q=q, fp64=True)
+    rgb, yf, st = c64.decode(idx, img.shape, original=img, stats=True, return_float=True)
+    ref_f = O.decode_array(idx, img.shape, B, q, return_float=True)
+    assert yf.dtype == np.float64 and np.array_equal(yf, ref_f)
+    assert int(st["sse"].sum()) == O.sse_int(img, rgb)
+    for c in range(3):
+        assert int(st["sse"][c]) == O.sse_int(img[..., c], rgb[..., c])
+    assert st["nsamples"] == img.size
+    assert abs(st["rmse"] - float(O.rmse(img, rgb))) < 1e-4
+    got, se = _codec(block_size=B, q=q).encode(img, stats=True)
+    nz, sabs, hist = O.index_stats(got)
+    assert se["nonzero"] == nz and se["sumabs"] == sabs and se["nindices"] == got.size
+    assert np.array_equal(se["hist"], hist)
+
+
+def test_batch_equals_single_frames_and_unaligned_pointers(torch_cuda):
+    t = torch_cuda
+    n, H, W = 5, 70, 150
+    frames = np.stack([O.synthetic_frame(H, W, 700 + i, "natural") for i in range(n)])
+    c = _codec(block_size=8, q=8)
+    ref = np.stack([O.encode_array(f, 8, 8) for f in frames])
+    assert np.array_equal(c.encode(frames), ref)
+    # device pointers at every byte alignment
+    for off in (0, 1, 2, 3, 5, 8, 13):
+        buf = t.zeros(frames.size + 64, dtype=t.uint8, device="cuda")
+        view = buf[off:off + frames.size].view(n, H, W, 3)
+        view.copy_(t.from_numpy(frames))
+        got = c.encode(view)
+        assert np.array_equal(got.cpu().numpy(), ref), off
+        ibuf = t.zeros(ref.size + 64, dtype=t.uint8, device="cuda")
+        iview = ibuf[off:off + ref.size].view(*ref.shape)
+        iview.copy_(t.from_numpy(ref))
+        dec = _codec(block_size=8, q=8, fp64=True).decode(iview, (H, W))
+        refd = np.stack([O.decode_array(r, (H, W, 3), 8, 8) for r in ref])
+        assert np.array_equal(dec.cpu().numpy(), refd), off
+
+
+def test_full_size_4k_properties(torch_cuda):
+    """BASELINE config 2 size (3840x2160): exact parity on one frame per q, plus
+    size-independent properties on the batch."""
+    t = torch_cuda
+    H, W = 2160, 3840
+    img = O.synthetic_frame(H, W, 2, "natural")
+    for q in (8, 16, 32, 64):
+        ref = O.encode_array(img, 8, q)
+        c = _codec(block_size=8, q=q)
+        got = c.encode(t.from_numpy(img).cuda())
+        assert np.array_equal(got.cpu().numpy(), ref), q
+        dec = _codec(block_size=8, q=q, fp64=True).decode(got, (H, W))
+        refd = O.decode_array(ref, img.shape, 8, q)
+        assert np.array_equal(dec.cpu().numpy(), refd), q
+        dec32 = c.decode(got, (H, W)).cpu().numpy()
+        assert np.abs(dec32.astype(np.int16) - refd.astype(np.int16)).max() <= 1
+        assert abs(O.psnr(img, dec32) - O.psnr(img, refd)) < 0.01
+    # B=32 pads 2160 -> 2176 (8 zero rows top and bottom)
+    ref = O.encode_array(img, 32, 32)
+    got = _codec(block_size=32, q=32).encode(t.from_numpy(img).cuda())
+    assert got.shape == (2176, 3840, 3) and np.array_equal(got.cpu().numpy(), ref)
+    # re-encoding a decoded frame with the same q is stable after one round (idempotence)
+    c = _codec(block_size=8, q=32)
+    d1 = c.decode(c.encode(t.from_numpy(img).cuda()), (H, W))
+    d2 = c.decode(c.encode(d1), (H, W))
+    d3 = c.decode(c.encode(d2), (H, W))
+    assert (d3 != d2).float().mean().item() <= (d2 != d1).float().mean().item() + 1e-9
+
+
+def test_errors_are_loud(torch_cuda):
+    from vcf_b200 import VcfbError, Codec
+    img = np.zeros((16, 16, 3), np.uint8)
+    with pytest.raises(ValueError):
+        Codec(block_size=7)
+    with pytest.raises(ValueError):
+        Codec(q=0)
+    with pytest.raises(ValueError):
+        Codec(block_size=8).decode(np.zeros((8, 8, 3), np.uint8), (16, 16))
+    from vcf_b200 import _lib
+    L = _lib.lib()
+    assert L.vcfb_encode_dev(None, 1, 16, 16, 8, 32.0, 0, 0, None, None, None, None) < 0
+    assert b"NULL" in L.vcfb_last_error()

@@ -1,0 +1,56 @@
+// Shared declarations of libvcfb200's translation units.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "vcfb200.h"
+
+namespace vcfb {
+
+// Geometry of one frame: src/2D-DCT.py:208-219 (padding) and :306-307 (subband size).
+struct Geom {
+  int H, W;       // un-padded frame
+  int Hp, Wp;     // padded to a multiple of B
+  int top, left;  // offsets of the centred frame inside the padded one
+  int ny, nx;     // blocks per column / row = subband size
+};
+
+struct EncArgs {
+  const uint8_t* rgb;
+  uint8_t* idx;
+  Geom g;
+  int n_frames;
+  double q, inv_q;
+  int q_pow2;
+  int color;
+  unsigned flags;
+  const double* weights;
+  unsigned long long* stats;
+};
+
+struct DecArgs {
+  const uint8_t* idx;
+  uint8_t* rgb;
+  void* y_out;
+  const uint8_t* original;
+  Geom g;
+  int n_frames;
+  double q;
+  int q_int;       // q as an integer when it is integral (numpy keeps int16 * int), else 0
+  int color;
+  unsigned flags;
+  const double* weights;
+  unsigned long long* stats;
+};
+
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+
+// general kernels (all B, float32 / float64): kernels_general.cu
+int launch_encode_general(const EncArgs& a, int B, cudaStream_t s);
+int launch_decode_general(const DecArgs& a, int B, cudaStream_t s);
+
+}  // namespace vcfb
