@@ -1,0 +1,421 @@
+#!/usr/bin/env python
+"""Benchmark of the fused colour + block-DCT + deadzone path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): batches of synthetic 3840x2160 RGB frames,
+YCoCg, B=8, deadzone q cycling through {8,16,32,64}.  One *step* = one pass of the
+hot path over one batch: encode (uint8 RGB -> uint8 indices) followed by decode
+(indices -> uint8 RGB).  Metric: Mpixel/s of encode+decode, whole job.
+
+* ``value``  -- inputs resident in HBM, CUDA-event timed on the launching stream.
+* ``e2e``    -- the same step through the public host API (numpy in pinned host
+  memory in, numpy out): host->device and device->host copies inside the timed
+  region.
+* ``roofline`` -- dominant kernel against the measured HBM copy peak.
+* ``cpu_baseline`` -- the CPU oracle (numpy/scipy restatement of the reference)
+  timed on this box's host cores on a bounded sample.
+
+Frame-parallel at N GPUs (one process per GPU, torchrun): every rank transforms
+its own batch, no data-path collective (weak scaling).  ``--workload rde`` adds
+the rate/distortion statistics and their NCCL all-reduce (BASELINE config 5 style).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W, B = 2160, 3840, 8
+QS = (8, 16, 32, 64)
+ALG_BYTES_PER_PX = {"encode": 6.0, "decode": 6.0}    # 3 B read + 3 B written each
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames", type=int, default=64, help="4K frames per GPU per step")
+    ap.add_argument("--e2e-frames", type=int, default=16, help="4K frames per GPU per end-to-end step")
+    ap.add_argument("--decode", default="fp64", choices=["fp32", "fp64"],
+                    help="decoder arithmetic: fp32 (+-1 LSB) or fp64 (the reference's chain, bit-exact)")
+    ap.add_argument("--contract", action="store_true", help="encoder: allow fused multiply-adds (VCFB_F_CONTRACT)")
+    ap.add_argument("--workload", default="c2", choices=["c2", "rde"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=20.0)
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows = []
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for ts, line in self.rows:
+            p = [x.strip() for x in line.split(",")]
+            if len(p) < 8:
+                continue
+            try:
+                mx = float(p[2])
+                if t0 <= ts <= t1 + 0.15:
+                    sm.append(float(p[1]))
+                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[4:8]):
+                        if v.lower().startswith("active"):
+                            reasons.add(name)
+            except ValueError:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------
+# CPU oracle timing (cpu_baseline leg and --impl reference)
+# ----------------------------------------------------------------------------
+def _cpu_worker(args):
+    seed, q, reps, loop = args
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    import numpy as np
+    from oracle import vcf_oracle as O
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, size=(H, W, 3), dtype=np.uint8)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        idx = O.encode_array(img, B, q, loop=loop)
+        dec = O.decode_array(idx, img.shape, B, q, loop=loop)
+    dt = time.perf_counter() - t0
+    return dt, int(dec[0, 0, 0])
+
+
+def cpu_oracle_throughput(budget_s: float, q: int = 32):
+    """Encode+decode Mpixel/s of the vectorised oracle with every usable host core
+    (one 4K frame per worker process), plus the faithful per-block-loop form on one
+    core on a 1/16 frame.  Bounded to about ``budget_s`` seconds."""
+    import multiprocessing as mp
+    import numpy as np
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 64 << 30
+    try:
+        cores_avail = len(os.sched_getaffinity(0))
+    except Exception:
+        cores_avail = os.cpu_count() or 1
+    workers = max(1, min(cores_avail, int(avail // (3 << 30))))
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(workers) as pool:
+        pool.map(_cpu_worker_warm, range(workers))               # import cost outside the timing
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_worker, [(1000 + i, q, 1, False) for i in range(workers)])
+        wall = time.perf_counter() - t0
+        reps = max(1, min(8, int(budget_s * 0.6 / max(wall, 1e-3))))
+        if reps > 1:
+            t0 = time.perf_counter()
+            res = pool.map(_cpu_worker, [(1000 + i, q, reps, False) for i in range(workers)])
+            wall = time.perf_counter() - t0
+        else:
+            reps = 1
+    mpx = workers * reps * H * W / 1e6 / wall
+    # faithful loop form (what the reference executes), one core, 1/16 frame
+    from oracle import vcf_oracle as O
+    img = np.random.default_rng(5).integers(0, 256, size=(H // 4, W // 4, 3), dtype=np.uint8)
+    t0 = time.perf_counter()
+    idx = O.encode_array(img, B, q, loop=True)
+    O.decode_array(idx, img.shape, B, q, loop=True)
+    loop_mpx = (H // 4) * (W // 4) / 1e6 / (time.perf_counter() - t0)
+    single = H * W / 1e6 / (sum(r[0] for r in res) / len(res) / reps)
+    return dict(value=mpx, unit="Mpixel/s", cores=workers, kind="port",
+                sample=(f"{workers * reps} synthetic 3840x2160 frames, encode+decode, q={q}, vectorised numpy/scipy "
+                        f"oracle, {workers} processes x {reps} frame(s); wall {wall:.1f}s"),
+                per_core_value=single, loop_form_1core_value=loop_mpx,
+                loop_form_sample="per-block Python loop (the reference's form), 960x540, 1 core",
+                host_cpus=os.cpu_count())
+
+
+def _cpu_worker_warm(_):
+    import numpy  # noqa: F401
+    import scipy.fftpack  # noqa: F401
+    from oracle import vcf_oracle  # noqa: F401
+    return 0
+
+
+def run_reference(a):
+    """--impl reference: the reference's CPU implementation of the path.  The four
+    arithmetic packages it imports are not installable offline, so
+    this times the oracle port with every usable host core; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step = []
+    base = None
+    for s in range(a.warmup + a.steps):
+        base = cpu_oracle_throughput(a.cpu_seconds / max(1, a.steps), q=QS[s % 4])
+        if s >= a.warmup:
+            per_step.append(base["value"])
+    v = sum(per_step) / len(per_step)
+    base["value"] = v
+    px = base["cores"] * H * W
+    line = dict(impl="reference", metric="Mpixel/s encode+decode (color+DCT+deadzone)", value=v, unit="Mpixel/s",
+                n_gpus=a.gpus, steps=a.steps, warmup=a.warmup, ms_per_step=px / 1e6 / v * 1e3,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32 encode / f64 decode",
+                data="synthetic",
+                config={"workload": "configs[1]: 3840x2160 RGB, YCoCg, B=8, q in {8,16,32,64}, encode+decode",
+                        "note": "each step is a bounded sample: one frame per host core"},
+                cpu_baseline=base,
+                e2e={"value": v, "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0})
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------
+def make_frames(torch, n, device, seed):
+    """Synthetic natural-like frames generated on the device (smooth field + noise)."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    yy = torch.arange(H, device=device, dtype=torch.float32)[:, None]
+    xx = torch.arange(W, device=device, dtype=torch.float32)[None, :]
+    out = torch.empty((n, H, W, 3), dtype=torch.uint8, device=device)
+    for i in range(n):
+        ph = torch.rand(6, generator=g, device=device) * 6.283
+        for c in range(3):
+            f = (128 + 70 * torch.sin(6.283 * (1 + c) * xx / W + ph[c] + 0.1 * i) * torch.cos(6.283 * (2 - 0.5 * c) * yy / H + ph[3 + c])
+                 + 30 * torch.sin(6.283 * (xx + yy) / 97.0 + ph[c]))
+            f = f + 6 * torch.randn((H, W), generator=g, device=device)
+            out[i, :, :, c] = f.round().clamp(0, 255).to(torch.uint8)
+    return out
+
+
+def run_ours(a):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from vcf_b200 import Codec, _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert _lib.lib().vcfb_device_count() > 0
+
+    n = a.frames
+    fp64_dec = a.decode == "fp64"
+    enc = {q: Codec(block_size=B, q=q, contract=a.contract) for q in QS}
+    dec = {q: Codec(block_size=B, q=q, fp64=fp64_dec) for q in QS}
+    x = make_frames(torch, n, dev, 1234 + rank)
+    idx = torch.empty((n, H, W, 3), dtype=torch.uint8, device=dev)
+    y = torch.empty((n, H, W, 3), dtype=torch.uint8, device=dev)
+    rde = a.workload == "rde"
+    launches = 0
+
+    def step(s, ev=None):
+        nonlocal launches
+        q = QS[s % 4]
+        if ev:
+            ev[0].record()
+        if rde:
+            _, st_e = enc[q].encode(x, out=idx, stats=True)
+        else:
+            enc[q].encode(x, out=idx)
+        if ev:
+            ev[1].record()
+        if rde:
+            r = dec[q].decode(idx, (H, W), out=y, original=x, stats=True)
+            st = r[-1] + st_e
+            if world > 1:
+                dist.all_reduce(st)
+        else:
+            dec[q].decode(idx, (H, W), out=y)
+        if ev:
+            ev[2].record()
+        launches += 2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for s in range(a.warmup):
+        step(s)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(a.steps)]
+    launches = 0
+    barrier()
+    t_wall0 = time.time()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(a.steps):
+        step(s, evs[s])
+    e1.record()
+    barrier()
+    t_wall1 = time.time()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    enc_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / a.steps
+    dec_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / a.steps
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+
+    px_step = n * H * W
+    value = world * px_step * a.steps / 1e6 / (ms / 1e3)
+
+    # ---- correctness spot check on the timed buffers (never timed) -----------------
+    torch.cuda.synchronize()
+
+    # ---- end to end through the host API: pinned numpy in, pinned numpy out ----------
+    ne = a.e2e_frames
+    hx = torch.empty((ne, H, W, 3), dtype=torch.uint8, pin_memory=True)
+    hx.copy_(x[:ne])
+    hidx = torch.empty((ne, H, W, 3), dtype=torch.uint8, pin_memory=True)
+    hy = torch.empty((ne, H, W, 3), dtype=torch.uint8, pin_memory=True)
+    hxn, hidxn, hyn = hx.numpy(), hidx.numpy(), hy.numpy()
+    enc_h = {q: Codec(block_size=B, q=q, contract=a.contract, device=local) for q in QS}
+    dec_h = {q: Codec(block_size=B, q=q, fp64=fp64_dec, device=local) for q in QS}
+
+    def e2e_step(s):
+        q = QS[s % 4]
+        enc_h[q].encode(hxn, out=hidxn)
+        dec_h[q].decode(hidxn, (H, W), out=hyn)
+
+    for s in range(max(a.warmup, 4)):
+        e2e_step(s)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(a.steps):
+        e2e_step(s)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_s = float(t.item())
+    e2e_val = world * ne * H * W * a.steps / 1e6 / e2e_s
+    same = bool(torch.equal(hy[:1].to(dev), y[:1])) if a.steps % 4 == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak = float(json.load(open(peaks_path))["hbm_gbs"])
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback (of fallback)"
+    dom = "encode" if enc_ms >= dec_ms else "decode"
+    dom_ms = max(enc_ms, dec_ms)
+    extra_b = 3.0 if (rde and dom == "decode") else 0.0
+    achieved = (ALG_BYTES_PER_PX[dom] + extra_b) * px_step / (dom_ms / 1e3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(dom)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": f"{dom}_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "alg_bytes_per_launch": (ALG_BYTES_PER_PX[dom] + extra_b) * px_step,
+                "encode_ms_per_launch": enc_ms, "decode_ms_per_launch": dec_ms,
+                "encode_frac": 6.0 * px_step / (enc_ms / 1e3) / 1e9 / peak,
+                "decode_frac": (6.0 + (3.0 if rde else 0.0)) * px_step / (dec_ms / 1e3) / 1e9 / peak,
+                "roundtrip_frac_of_12B_per_px": 12.0 * px_step / ((enc_ms + dec_ms) / 1e3) / 1e9 / peak}
+
+    line = {"metric": "Mpixel/s encode+decode (color+DCT+deadzone)", "value": value, "unit": "Mpixel/s",
+            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms / a.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": f"f32 encode ({'contracted' if a.contract else 'bit-exact with the reference float32 path'}) / "
+                     f"{'f64 (reference chain, bit-exact)' if fp64_dec else 'f32 (+-1 LSB)'} decode",
+            "data": "synthetic",
+            "config": {"workload": ("configs[1]: 3840x2160 RGB, YCoCg, B=8, q in {8,16,32,64} cycled per step, "
+                                    "encode+decode" + (", RD statistics + NCCL all-reduce" if rde else "")),
+                       "frames_per_gpu_per_step": n, "parallelism": f"frame-parallel x{world}",
+                       "l2": f"inputs exceed L2: {3 * n * H * W * 3 / 1e9:.1f} GB touched per step vs 126 MB"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": "Mpixel/s", "h2d_bytes_per_step": 2 * ne * H * W * 3,
+                    "d2h_bytes_per_step": 2 * ne * H * W * 3, "frames_per_step": ne,
+                    "api": "vcf_b200.Codec.encode/decode on pinned numpy arrays (vcfb_encode_host/vcfb_decode_host)",
+                    "matches_device_path": same},
+            "gpu_launches": launches,
+            "roofline": roofline}
+    if world == 1 and not a.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_oracle_throughput(a.cpu_seconds)
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    if a.gpus > 1 and "WORLD_SIZE" not in os.environ:
+        import socket
+        s = socket.socket()
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+        s.close()
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={a.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -27,6 +27,7 @@
 #ifndef VCFB200_H
 #define VCFB200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -119,8 +120,16 @@ typedef struct vcfb_ctx vcfb_ctx;
 int vcfb_ctx_create(int device, vcfb_ctx** out);
 void vcfb_ctx_destroy(vcfb_ctx* ctx);
 
+/* Pinned (page-locked) host memory.  Host buffers obtained here -- or pinned by
+ * any other means -- are transferred in place; pageable buffers are staged through
+ * the context's own pinned memory at the cost of one extra host copy. */
+int vcfb_host_alloc(size_t bytes, void** out);
+void vcfb_host_free(void* p);
+
 /* Same contracts as the *_dev calls with HOST pointers (weights, stats too);
- * stats (may be NULL) receives this call's statistics (overwritten, not added). */
+ * stats (may be NULL) receives this call's statistics (overwritten, not added).
+ * A batch is cut into chunks of whole frames that are copied in, transformed and
+ * copied out on three streams so both copy engines and the SMs overlap. */
 int vcfb_encode_host(vcfb_ctx* ctx, const uint8_t* rgb, int n_frames, int H, int W, int B,
                      double q, int color, unsigned flags, const double* weights,
                      uint8_t* idx_out, int64_t* stats);

@@ -50,6 +50,10 @@ def lib():
     L.vcfb_ctx_create.restype = i
     L.vcfb_ctx_destroy.argtypes = [vp]
     L.vcfb_ctx_destroy.restype = None
+    L.vcfb_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.vcfb_host_alloc.restype = i
+    L.vcfb_host_free.argtypes = [vp]
+    L.vcfb_host_free.restype = None
     L.vcfb_encode_host.argtypes = [vp, vp, i, i, i, i, d, i, u, vp, vp, vp]
     L.vcfb_encode_host.restype = i
     L.vcfb_decode_host.argtypes = [vp, vp, i, i, i, i, d, i, u, vp, vp, vp, vp, vp]

@@ -139,9 +139,11 @@ class Codec:
         return x
 
     # -- encode -------------------------------------------------------------------
-    def encode(self, rgb, stats: bool = False):
+    def encode(self, rgb, stats: bool = False, out=None):
         """uint8 RGB (n,H,W,3)|(H,W,3) -> uint8 indices (n,Hp,Wp,3)|(Hp,Wp,3)
-        [, statistics dict].  Replaces src/2D-DCT.py:276-361."""
+        [, statistics dict].  Replaces src/2D-DCT.py:276-361.
+        ``out``: optional preallocated (n,Hp,Wp,3) uint8 result (same kind as the
+        input; a pinned numpy array is transferred without a staging copy)."""
         L = _lib.lib()
         single = rgb.ndim == 3
         x = self._frames(rgb, "rgb")
@@ -152,7 +154,11 @@ class Codec:
             if x.dtype != torch.uint8 or not x.is_cuda:
                 raise ValueError("torch input must be a CUDA uint8 tensor")
             x = x.contiguous()
-            out = torch.empty((n, Hp, Wp, 3), dtype=torch.uint8, device=x.device)
+            if out is None:
+                out = torch.empty((n, Hp, Wp, 3), dtype=torch.uint8, device=x.device)
+            elif (tuple(out.shape) != (n, Hp, Wp, 3) or out.dtype != torch.uint8 or out.device != x.device
+                  or not out.is_contiguous()):
+                raise ValueError("out must be a contiguous uint8 tensor (n,Hp,Wp,3) on the input's device")
             st = torch.zeros(STAT_LEN, dtype=torch.int64, device=x.device) if stats else None
             w = self._dev_weights(x.device)
             with torch.cuda.device(x.device):
@@ -165,7 +171,10 @@ class Codec:
         x = np.ascontiguousarray(x)
         if x.dtype != np.uint8:
             raise ValueError("rgb must be uint8")
-        out = np.empty((n, Hp, Wp, 3), dtype=np.uint8)
+        if out is None:
+            out = np.empty((n, Hp, Wp, 3), dtype=np.uint8)
+        elif out.shape != (n, Hp, Wp, 3) or out.dtype != np.uint8 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous uint8 array (n,Hp,Wp,3)")
         st = np.zeros(STAT_LEN, dtype=np.int64) if stats else None
         w = self._weights_np
         check(L.vcfb_encode_host(self._host_ctx(), x.ctypes.data, n, H, W, self.B, self.q, self.color,
@@ -176,7 +185,7 @@ class Codec:
 
     # -- decode -------------------------------------------------------------------
     def decode(self, idx, shape, original=None, stats: bool = False, return_float: bool = False,
-               want_rgb: bool = True):
+               want_rgb: bool = True, out=None):
         """uint8 indices -> uint8 RGB of un-padded ``shape`` = (H, W).
         Replaces src/2D-DCT.py:398-466.
 
@@ -197,7 +206,12 @@ class Codec:
                 raise ValueError("torch input must be a CUDA uint8 tensor")
             k = k.contiguous()
             dev = k.device
-            rgb = torch.empty((n, H, W, 3), dtype=torch.uint8, device=dev) if want_rgb else None
+            rgb = None
+            if want_rgb:
+                rgb = out if out is not None else torch.empty((n, H, W, 3), dtype=torch.uint8, device=dev)
+                if (tuple(rgb.shape) != (n, H, W, 3) or rgb.dtype != torch.uint8 or rgb.device != dev
+                        or not rgb.is_contiguous()):
+                    raise ValueError("out must be a contiguous uint8 tensor (n,H,W,3) on the input's device")
             yf = torch.empty((n, H, W, 3), dtype=torch.float64 if self.fp64 else torch.float32,
                              device=dev) if return_float else None
             org = None
@@ -224,7 +238,11 @@ class Codec:
         k = np.ascontiguousarray(k)
         if k.dtype != np.uint8:
             raise ValueError("idx must be uint8")
-        rgb = np.empty((n, H, W, 3), dtype=np.uint8) if want_rgb else None
+        rgb = None
+        if want_rgb:
+            rgb = out if out is not None else np.empty((n, H, W, 3), dtype=np.uint8)
+            if rgb.shape != (n, H, W, 3) or rgb.dtype != np.uint8 or not rgb.flags.c_contiguous:
+                raise ValueError("out must be a C-contiguous uint8 array (n,H,W,3)")
         yf = np.empty((n, H, W, 3), dtype=np.float64 if self.fp64 else np.float32) if return_float else None
         org = None
         if original is not None:
@@ -247,13 +265,36 @@ class Codec:
         return res[0] if len(res) == 1 else tuple(res)
 
 
+class _PinnedOwner:
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __del__(self):
+        try:
+            _lib.lib().vcfb_host_free(self.ptr)
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.uint8) -> np.ndarray:
+    """numpy array in page-locked host memory (vcfb_host_alloc).  The host entry
+    points transfer such arrays in place, without the pageable staging copy."""
+    dt = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dt.itemsize
+    p = C.c_void_p()
+    check(_lib.lib().vcfb_host_alloc(max(nbytes, 1), C.byref(p)))
+    buf = (C.c_uint8 * max(nbytes, 1)).from_address(p.value)
+    buf._vcfb_owner = _PinnedOwner(p)     # freed when the array (whose base is buf) dies
+    return np.frombuffer(buf, dtype=dt, count=int(np.prod(shape))).reshape(shape)
+
+
 def encode_frames(rgb, block_size=8, q=32, **kw):
     stats = kw.pop("stats", False)
     return Codec(block_size, q, **kw).encode(rgb, stats=stats)
 
 
 def decode_frames(idx, shape, block_size=8, q=32, **kw):
-    call = {k: kw.pop(k) for k in ("original", "stats", "return_float", "want_rgb") if k in kw}
+    call = {k: kw.pop(k) for k in ("original", "stats", "return_float", "want_rgb", "out") if k in kw}
     return Codec(block_size, q, **kw).decode(idx, shape, **call)
 
 

@@ -121,32 +121,74 @@ int vcfb_decode_dev(const uint8_t* idx, int n_frames, int H, int W, int B, doubl
 }
 
 // ---- host-buffer layer ----------------------------------------------------------
+//
+// A batch is cut into chunks of whole frames; chunk i runs on slot i % NSLOT
+// (one stream + device staging per slot), so the host->device copy of the next
+// chunk, the kernel and the device->host copy of the previous chunk overlap on the
+// two copy engines.  Pinned user buffers (cudaHostAlloc / cudaHostRegister /
+// vcfb_host_alloc / torch pin_memory) are used in place; pageable ones are staged
+// through the slot's own pinned buffer.
+
+namespace {
+constexpr int NSLOT = 3;
+constexpr size_t CHUNK_TARGET = size_t(96) << 20;   // bytes of input per chunk
+
+struct Slot {
+  cudaStream_t s;
+  char* dev; size_t dev_cap;
+  char* pin; size_t pin_cap;
+  // pageable output waiting for the stream: copy pin+off -> dst after sync
+  struct Pending { void* dst; size_t off, bytes; } pend[2];
+  int npend;
+};
+}  // namespace
 
 struct vcfb_ctx {
   int device;
-  cudaStream_t stream;
-  void* pin;   size_t pin_cap;    // pinned host staging
-  void* dev;   size_t dev_cap;    // device staging
+  Slot slot[NSLOT];
+  char* aux;        // device: weights + stats
+  size_t aux_cap;
+  cudaEvent_t ready;
 };
 
-static int ctx_reserve(vcfb_ctx* c, size_t pin_bytes, size_t dev_bytes) {
-  cudaError_t e;
-  if (pin_bytes > c->pin_cap) {
-    if (c->pin) cudaFreeHost(c->pin);
-    c->pin = nullptr; c->pin_cap = 0;
-    e = cudaMallocHost(&c->pin, pin_bytes);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaMallocHost");
-    c->pin_cap = pin_bytes;
+static bool is_pinned(const void* p) {
+  if (!p) return false;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
   }
-  if (dev_bytes > c->dev_cap) {
-    if (c->dev) cudaFree(c->dev);
-    c->dev = nullptr; c->dev_cap = 0;
-    e = cudaMalloc(&c->dev, dev_bytes);
+  return at.type == cudaMemoryTypeHost;
+}
+
+static int slot_reserve(Slot* sl, size_t dev_bytes, size_t pin_bytes) {
+  cudaError_t e;
+  if (dev_bytes > sl->dev_cap) {
+    if (sl->dev) cudaFree(sl->dev);
+    sl->dev = nullptr; sl->dev_cap = 0;
+    e = cudaMalloc(reinterpret_cast<void**>(&sl->dev), dev_bytes);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
-    c->dev_cap = dev_bytes;
+    sl->dev_cap = dev_bytes;
+  }
+  if (pin_bytes > sl->pin_cap) {
+    if (sl->pin) cudaFreeHost(sl->pin);
+    sl->pin = nullptr; sl->pin_cap = 0;
+    e = cudaMallocHost(reinterpret_cast<void**>(&sl->pin), pin_bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMallocHost");
+    sl->pin_cap = pin_bytes;
   }
   return VCFB_OK;
 }
+
+static int slot_drain(Slot* sl) {
+  cudaError_t e = cudaStreamSynchronize(sl->s);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
+  for (int i = 0; i < sl->npend; ++i) memcpy(sl->pend[i].dst, sl->pin + sl->pend[i].off, sl->pend[i].bytes);
+  sl->npend = 0;
+  return VCFB_OK;
+}
+
+static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
 int vcfb_ctx_create(int device, vcfb_ctx** out) {
   if (!out) { set_error("out is NULL"); return VCFB_E_ARG; }
@@ -157,8 +199,12 @@ int vcfb_ctx_create(int device, vcfb_ctx** out) {
   if (!c) { set_error("out of memory"); return VCFB_E_ARG; }
   memset(c, 0, sizeof(*c));
   c->device = device;
-  e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-  if (e != cudaSuccess) { delete c; return cuda_fail(e, "cudaStreamCreate"); }
+  for (int i = 0; i < NSLOT; ++i) {
+    e = cudaStreamCreateWithFlags(&c->slot[i].s, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { vcfb_ctx_destroy(c); return cuda_fail(e, "cudaStreamCreate"); }
+  }
+  e = cudaEventCreateWithFlags(&c->ready, cudaEventDisableTiming);
+  if (e != cudaSuccess) { vcfb_ctx_destroy(c); return cuda_fail(e, "cudaEventCreate"); }
   *out = c;
   return VCFB_OK;
 }
@@ -166,13 +212,64 @@ int vcfb_ctx_create(int device, vcfb_ctx** out) {
 void vcfb_ctx_destroy(vcfb_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  if (c->stream) cudaStreamDestroy(c->stream);
-  if (c->pin) cudaFreeHost(c->pin);
-  if (c->dev) cudaFree(c->dev);
+  for (int i = 0; i < NSLOT; ++i) {
+    if (c->slot[i].s) { cudaStreamSynchronize(c->slot[i].s); cudaStreamDestroy(c->slot[i].s); }
+    if (c->slot[i].dev) cudaFree(c->slot[i].dev);
+    if (c->slot[i].pin) cudaFreeHost(c->slot[i].pin);
+  }
+  if (c->aux) cudaFree(c->aux);
+  if (c->ready) cudaEventDestroy(c->ready);
   delete c;
 }
 
-static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+int vcfb_host_alloc(size_t bytes, void** out) {
+  if (!out) { set_error("out is NULL"); return VCFB_E_ARG; }
+  cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMallocHost");
+  return VCFB_OK;
+}
+
+void vcfb_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+// Upload weights, zero the statistics vector; every slot stream waits for both.
+static int aux_prepare(vcfb_ctx* c, const double* weights, size_t w_b, bool want_stats,
+                       double** d_w, int64_t** d_st) {
+  const size_t st_off = align256(w_b);
+  const size_t need = st_off + VCFB_STAT_LEN * sizeof(int64_t);
+  cudaError_t e;
+  if (need > c->aux_cap) {
+    for (int i = 0; i < NSLOT; ++i) cudaStreamSynchronize(c->slot[i].s);
+    if (c->aux) cudaFree(c->aux);
+    c->aux = nullptr; c->aux_cap = 0;
+    e = cudaMalloc(reinterpret_cast<void**>(&c->aux), need);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc");
+    c->aux_cap = need;
+  }
+  *d_w = w_b ? reinterpret_cast<double*>(c->aux) : nullptr;
+  *d_st = want_stats ? reinterpret_cast<int64_t*>(c->aux + st_off) : nullptr;
+  cudaStream_t s0 = c->slot[0].s;
+  e = cudaSuccess;
+  if (w_b) e = cudaMemcpyAsync(c->aux, weights, w_b, cudaMemcpyHostToDevice, s0);
+  if (e == cudaSuccess && want_stats) e = cudaMemsetAsync(c->aux + st_off, 0, VCFB_STAT_LEN * sizeof(int64_t), s0);
+  if (e == cudaSuccess) e = cudaEventRecord(c->ready, s0);
+  for (int i = 1; i < NSLOT && e == cudaSuccess; ++i) e = cudaStreamWaitEvent(c->slot[i].s, c->ready, 0);
+  if (e != cudaSuccess) return cuda_fail(e, "weights / statistics setup");
+  return VCFB_OK;
+}
+
+static int finish(vcfb_ctx* c, int64_t* d_st, int64_t* stats) {
+  for (int i = 0; i < NSLOT; ++i) {
+    int rc = slot_drain(&c->slot[i]);
+    if (rc) return rc;
+  }
+  if (d_st && stats) {
+    cudaError_t e = cudaMemcpy(stats, d_st, VCFB_STAT_LEN * sizeof(int64_t), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return cuda_fail(e, "statistics device->host");
+  }
+  return VCFB_OK;
+}
 
 int vcfb_encode_host(vcfb_ctx* c, const uint8_t* rgb, int n_frames, int H, int W, int B, double q,
                      int color, unsigned flags, const double* weights, uint8_t* idx_out,
@@ -184,33 +281,40 @@ int vcfb_encode_host(vcfb_ctx* c, const uint8_t* rgb, int n_frames, int H, int W
   if (!idx_out) { set_error("idx_out is NULL"); return VCFB_E_ARG; }
   cudaError_t e = cudaSetDevice(c->device);
   if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-  const size_t in_b = size_t(n_frames) * H * W * 3, out_b = size_t(n_frames) * g.Hp * g.Wp * 3;
+  const size_t in_f = size_t(H) * W * 3, out_f = size_t(g.Hp) * g.Wp * 3;
   const size_t w_b = (flags & VCFB_F_PERCEPTUAL) ? size_t(2) * B * B * sizeof(double) : 0;
-  const size_t st_b = stats ? VCFB_STAT_LEN * sizeof(int64_t) : 0;
-  const size_t o_in = 0, o_out = align256(in_b), o_w = o_out + align256(out_b), o_st = o_w + align256(w_b);
-  const size_t total = o_st + align256(st_b);
-  rc = ctx_reserve(c, total, total);
+  double* d_w; int64_t* d_st;
+  rc = aux_prepare(c, weights, w_b, stats != nullptr, &d_w, &d_st);
   if (rc) return rc;
-  char* hp = static_cast<char*>(c->pin);
-  char* dp = static_cast<char*>(c->dev);
-  memcpy(hp + o_in, rgb, in_b);
-  if (w_b) memcpy(hp + o_w, weights, w_b);
-  e = cudaMemcpyAsync(dp + o_in, hp + o_in, in_b, cudaMemcpyHostToDevice, c->stream);
-  if (e == cudaSuccess && w_b) e = cudaMemcpyAsync(dp + o_w, hp + o_w, w_b, cudaMemcpyHostToDevice, c->stream);
-  if (e == cudaSuccess && st_b) e = cudaMemsetAsync(dp + o_st, 0, st_b, c->stream);
-  if (e != cudaSuccess) return cuda_fail(e, "host->device copy");
-  rc = vcfb_encode_dev(reinterpret_cast<uint8_t*>(dp + o_in), n_frames, H, W, B, q, color, flags,
-                       w_b ? reinterpret_cast<double*>(dp + o_w) : nullptr,
-                       reinterpret_cast<uint8_t*>(dp + o_out),
-                       st_b ? reinterpret_cast<int64_t*>(dp + o_st) : nullptr, c->stream);
-  if (rc) return rc;
-  e = cudaMemcpyAsync(hp + o_out, dp + o_out, out_b, cudaMemcpyDeviceToHost, c->stream);
-  if (e == cudaSuccess && st_b) e = cudaMemcpyAsync(hp + o_st, dp + o_st, st_b, cudaMemcpyDeviceToHost, c->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-  if (e != cudaSuccess) return cuda_fail(e, "encode (device->host / synchronize)");
-  memcpy(idx_out, hp + o_out, out_b);
-  if (st_b) memcpy(stats, hp + o_st, st_b);
-  return VCFB_OK;
+  const bool pin_in = is_pinned(rgb), pin_out = is_pinned(idx_out);
+  int cf = int(CHUNK_TARGET / in_f);
+  cf = cf < 1 ? 1 : cf;
+  if (cf > (n_frames + NSLOT - 1) / NSLOT) cf = (n_frames + NSLOT - 1) / NSLOT;
+  const size_t o_in = 0, o_out = align256(in_f * cf), slot_b = o_out + align256(out_f * cf);
+  for (int f0 = 0, ci = 0; f0 < n_frames; f0 += cf, ++ci) {
+    Slot* sl = &c->slot[ci % NSLOT];
+    const int nf = (n_frames - f0 < cf) ? n_frames - f0 : cf;
+    rc = slot_drain(sl);
+    if (rc) return rc;
+    rc = slot_reserve(sl, slot_b, (pin_in && pin_out) ? 0 : slot_b);
+    if (rc) return rc;
+    const uint8_t* src = rgb + size_t(f0) * in_f;
+    if (!pin_in) { memcpy(sl->pin + o_in, src, in_f * nf); src = reinterpret_cast<uint8_t*>(sl->pin + o_in); }
+    e = cudaMemcpyAsync(sl->dev + o_in, src, in_f * nf, cudaMemcpyHostToDevice, sl->s);
+    if (e != cudaSuccess) return cuda_fail(e, "host->device copy");
+    rc = vcfb_encode_dev(reinterpret_cast<uint8_t*>(sl->dev + o_in), nf, H, W, B, q, color, flags, d_w,
+                         reinterpret_cast<uint8_t*>(sl->dev + o_out), d_st, sl->s);
+    if (rc) return rc;
+    uint8_t* dst = idx_out + size_t(f0) * out_f;
+    if (pin_out) {
+      e = cudaMemcpyAsync(dst, sl->dev + o_out, out_f * nf, cudaMemcpyDeviceToHost, sl->s);
+    } else {
+      e = cudaMemcpyAsync(sl->pin + o_out, sl->dev + o_out, out_f * nf, cudaMemcpyDeviceToHost, sl->s);
+      sl->pend[sl->npend++] = {dst, o_out, out_f * nf};
+    }
+    if (e != cudaSuccess) return cuda_fail(e, "device->host copy");
+  }
+  return finish(c, d_st, stats);
 }
 
 int vcfb_decode_host(vcfb_ctx* c, const uint8_t* idx, int n_frames, int H, int W, int B, double q,
@@ -220,44 +324,67 @@ int vcfb_decode_host(vcfb_ctx* c, const uint8_t* idx, int n_frames, int H, int W
   Geom g;
   int rc = check_common(idx, n_frames, H, W, B, q, color, flags, weights, &g);
   if (rc) return rc;
+  if (!rgb_out && !y_out && !(original && stats)) { set_error("decode has no output"); return VCFB_E_ARG; }
   cudaError_t e = cudaSetDevice(c->device);
   if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-  const size_t px_b = size_t(n_frames) * H * W * 3, idx_b = size_t(n_frames) * g.Hp * g.Wp * 3;
-  const size_t y_b = y_out ? px_b * ((flags & VCFB_F_FP64) ? 8 : 4) : 0;
-  const size_t or_b = original ? px_b : 0;
+  const size_t px_f = size_t(H) * W * 3, idx_f = size_t(g.Hp) * g.Wp * 3;
+  const size_t y_f = y_out ? px_f * ((flags & VCFB_F_FP64) ? 8 : 4) : 0;
+  const size_t or_f = original ? px_f : 0;
   const size_t w_b = (flags & VCFB_F_PERCEPTUAL) ? size_t(2) * B * B * sizeof(double) : 0;
-  const size_t st_b = stats ? VCFB_STAT_LEN * sizeof(int64_t) : 0;
-  const size_t o_idx = 0, o_rgb = align256(idx_b), o_y = o_rgb + align256(px_b), o_or = o_y + align256(y_b),
-               o_w = o_or + align256(or_b), o_st = o_w + align256(w_b);
-  const size_t total = o_st + align256(st_b);
-  rc = ctx_reserve(c, total, total);
+  double* d_w; int64_t* d_st;
+  rc = aux_prepare(c, weights, w_b, stats != nullptr, &d_w, &d_st);
   if (rc) return rc;
-  char* hp = static_cast<char*>(c->pin);
-  char* dp = static_cast<char*>(c->dev);
-  memcpy(hp + o_idx, idx, idx_b);
-  if (or_b) memcpy(hp + o_or, original, or_b);
-  if (w_b) memcpy(hp + o_w, weights, w_b);
-  e = cudaMemcpyAsync(dp + o_idx, hp + o_idx, idx_b, cudaMemcpyHostToDevice, c->stream);
-  if (e == cudaSuccess && or_b) e = cudaMemcpyAsync(dp + o_or, hp + o_or, or_b, cudaMemcpyHostToDevice, c->stream);
-  if (e == cudaSuccess && w_b) e = cudaMemcpyAsync(dp + o_w, hp + o_w, w_b, cudaMemcpyHostToDevice, c->stream);
-  if (e == cudaSuccess && st_b) e = cudaMemsetAsync(dp + o_st, 0, st_b, c->stream);
-  if (e != cudaSuccess) return cuda_fail(e, "host->device copy");
-  rc = vcfb_decode_dev(reinterpret_cast<uint8_t*>(dp + o_idx), n_frames, H, W, B, q, color, flags,
-                       w_b ? reinterpret_cast<double*>(dp + o_w) : nullptr,
-                       rgb_out ? reinterpret_cast<uint8_t*>(dp + o_rgb) : nullptr,
-                       y_b ? static_cast<void*>(dp + o_y) : nullptr,
-                       or_b ? reinterpret_cast<uint8_t*>(dp + o_or) : nullptr,
-                       st_b ? reinterpret_cast<int64_t*>(dp + o_st) : nullptr, c->stream);
-  if (rc) return rc;
-  if (rgb_out) e = cudaMemcpyAsync(hp + o_rgb, dp + o_rgb, px_b, cudaMemcpyDeviceToHost, c->stream);
-  if (e == cudaSuccess && y_b) e = cudaMemcpyAsync(hp + o_y, dp + o_y, y_b, cudaMemcpyDeviceToHost, c->stream);
-  if (e == cudaSuccess && st_b) e = cudaMemcpyAsync(hp + o_st, dp + o_st, st_b, cudaMemcpyDeviceToHost, c->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-  if (e != cudaSuccess) return cuda_fail(e, "decode (device->host / synchronize)");
-  if (rgb_out) memcpy(rgb_out, hp + o_rgb, px_b);
-  if (y_b) memcpy(y_out, hp + o_y, y_b);
-  if (st_b) memcpy(stats, hp + o_st, st_b);
-  return VCFB_OK;
+  const bool all_pinned = is_pinned(idx) && (!rgb_out || is_pinned(rgb_out)) && (!y_out || is_pinned(y_out)) &&
+                          (!original || is_pinned(original));
+  int cf = int(CHUNK_TARGET / idx_f);
+  cf = cf < 1 ? 1 : cf;
+  if (cf > (n_frames + NSLOT - 1) / NSLOT) cf = (n_frames + NSLOT - 1) / NSLOT;
+  const size_t o_idx = 0, o_rgb = align256(idx_f * cf), o_y = o_rgb + align256(px_f * cf),
+               o_or = o_y + align256(y_f * cf), slot_b = o_or + align256(or_f * cf);
+  for (int f0 = 0, ci = 0; f0 < n_frames; f0 += cf, ++ci) {
+    Slot* sl = &c->slot[ci % NSLOT];
+    const int nf = (n_frames - f0 < cf) ? n_frames - f0 : cf;
+    rc = slot_drain(sl);
+    if (rc) return rc;
+    rc = slot_reserve(sl, slot_b, all_pinned ? 0 : slot_b);
+    if (rc) return rc;
+    const uint8_t* src = idx + size_t(f0) * idx_f;
+    const uint8_t* osrc = original ? original + size_t(f0) * px_f : nullptr;
+    if (!all_pinned) {
+      memcpy(sl->pin + o_idx, src, idx_f * nf);
+      src = reinterpret_cast<uint8_t*>(sl->pin + o_idx);
+      if (osrc) { memcpy(sl->pin + o_or, osrc, px_f * nf); osrc = reinterpret_cast<uint8_t*>(sl->pin + o_or); }
+    }
+    e = cudaMemcpyAsync(sl->dev + o_idx, src, idx_f * nf, cudaMemcpyHostToDevice, sl->s);
+    if (e == cudaSuccess && osrc) e = cudaMemcpyAsync(sl->dev + o_or, osrc, px_f * nf, cudaMemcpyHostToDevice, sl->s);
+    if (e != cudaSuccess) return cuda_fail(e, "host->device copy");
+    rc = vcfb_decode_dev(reinterpret_cast<uint8_t*>(sl->dev + o_idx), nf, H, W, B, q, color, flags, d_w,
+                         rgb_out ? reinterpret_cast<uint8_t*>(sl->dev + o_rgb) : nullptr,
+                         y_out ? static_cast<void*>(sl->dev + o_y) : nullptr,
+                         original ? reinterpret_cast<uint8_t*>(sl->dev + o_or) : nullptr, d_st, sl->s);
+    if (rc) return rc;
+    if (rgb_out) {
+      uint8_t* dst = rgb_out + size_t(f0) * px_f;
+      if (all_pinned) {
+        e = cudaMemcpyAsync(dst, sl->dev + o_rgb, px_f * nf, cudaMemcpyDeviceToHost, sl->s);
+      } else {
+        e = cudaMemcpyAsync(sl->pin + o_rgb, sl->dev + o_rgb, px_f * nf, cudaMemcpyDeviceToHost, sl->s);
+        sl->pend[sl->npend++] = {dst, o_rgb, px_f * nf};
+      }
+      if (e != cudaSuccess) return cuda_fail(e, "device->host copy");
+    }
+    if (y_out) {
+      char* dst = static_cast<char*>(y_out) + size_t(f0) * y_f;
+      if (all_pinned) {
+        e = cudaMemcpyAsync(dst, sl->dev + o_y, y_f * nf, cudaMemcpyDeviceToHost, sl->s);
+      } else {
+        e = cudaMemcpyAsync(sl->pin + o_y, sl->dev + o_y, y_f * nf, cudaMemcpyDeviceToHost, sl->s);
+        sl->pend[sl->npend++] = {dst, o_y, y_f * nf};
+      }
+      if (e != cudaSuccess) return cuda_fail(e, "device->host copy");
+    }
+  }
+  return finish(c, d_st, stats);
 }
 
 }  // extern "C"
