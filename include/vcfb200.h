@@ -77,6 +77,11 @@ extern "C" {
 int vcfb_version(void);
 const char* vcfb_last_error(void);
 
+/* Name of the kernel family the calling thread launched last ("enc8_fast",
+ * "encode_general", "decode_general", ...): lets tests and benchmarks assert which
+ * code path served a request. */
+const char* vcfb_last_kernel(void);
+
 /* Number of CUDA devices visible (0 if none / no driver). */
 int vcfb_device_count(void);
 

@@ -240,3 +240,57 @@ def test_errors_are_loud(torch_cuda):
     L = _lib.lib()
     assert L.vcfb_encode_dev(None, 1, 16, 16, 8, 32.0, 0, 0, None, None, None, None) < 0
     assert b"NULL" in L.vcfb_last_error()
+
+
+FAST_SHAPES = [(8, 128), (24, 384), (16, 512), (40, 1024), (13, 256), (1080, 1920), (61, 640)]
+
+
+@pytest.mark.parametrize("q", [1, 8, 12, 32, 64, 100])
+def test_fast_encode_path_exact(q, torch_cuda):
+    """The TMA fast path (B=8, W%16==0, nx%16==0) must be taken and must be bit-exact,
+    including partial tiles (W % 384 != 0), vertical padding (H % 8 != 0) and batches."""
+    from vcf_b200 import _lib
+    t = torch_cuda
+    for si, (H, W) in enumerate(FAST_SHAPES):
+        n = 3 if H * W < 200000 else 1
+        frames = np.stack([O.synthetic_frame(H, W, 900 + 10 * si + i, "noise" if i % 2 else "natural") for i in range(n)])
+        ref = np.stack([O.encode_array(f, 8, q) for f in frames])
+        got = _codec(block_size=8, q=q).encode(t.from_numpy(frames).cuda())
+        assert _lib.last_kernel() == "enc8_fast", (H, W, _lib.last_kernel())
+        assert np.array_equal(got.cpu().numpy(), ref), (H, W, q, int((got.cpu().numpy() != ref).sum()))
+    # not eligible -> general kernel, still exact
+    img = O.synthetic_frame(64, 96, 5, "natural")
+    got = _codec(block_size=8, q=q).encode(t.from_numpy(img).cuda())
+    assert _lib.last_kernel() == "encode_general"
+    assert np.array_equal(got.cpu().numpy(), O.encode_array(img, 8, q))
+
+
+@pytest.mark.parametrize("q", [1, 8, 12, 32, 64, 255])
+def test_fast_decode_path(q, torch_cuda):
+    """TMA decode fast path: float64 mode bit-exact with the reference chain, float32
+    mode within +-1 LSB; partial tiles, vertical padding (cropped rows), batches, and
+    arbitrary (non-encoder) index arrays."""
+    from vcf_b200 import _lib
+    t = torch_cuda
+    rng = np.random.default_rng(q)
+    for si, (H, W) in enumerate(FAST_SHAPES):
+        n = 3 if H * W < 200000 else 1
+        frames = np.stack([O.synthetic_frame(H, W, 950 + 10 * si + i, "noise" if i % 2 else "natural") for i in range(n)])
+        idx = np.stack([O.encode_array(f, 8, q) for f in frames])
+        if si % 2:
+            idx[-1] = rng.integers(0, 256, size=idx[-1].shape, dtype=np.uint8)
+        ref = np.stack([O.decode_array(k, (H, W, 3), 8, q) for k in idx])
+        got = _codec(block_size=8, q=q, fp64=True).decode(t.from_numpy(idx).cuda(), (H, W))
+        want = "dec8_fast" if H % 8 == 0 else "decode_general"     # vertical padding -> general kernel
+        assert _lib.last_kernel() == want, (H, W, _lib.last_kernel())
+        assert np.array_equal(got.cpu().numpy(), ref), (H, W, q, int((got.cpu().numpy() != ref).sum()))
+        for contract in (False, True):
+            g32 = _codec(block_size=8, q=q, contract=contract).decode(t.from_numpy(idx).cuda(), (H, W))
+            assert _lib.last_kernel() == want
+            assert np.abs(g32.cpu().numpy().astype(np.int16) - ref.astype(np.int16)).max() <= 1
+    # q too large for the fast path -> general kernel (int16 wrap semantics), still exact
+    img = O.synthetic_frame(16, 128, 7, "natural")
+    idx = O.encode_array(img, 8, 300)
+    got = _codec(block_size=8, q=300, fp64=True).decode(t.from_numpy(idx).cuda(), (16, 128))
+    assert _lib.last_kernel() == "decode_general"
+    assert np.array_equal(got.cpu().numpy(), O.decode_array(idx, img.shape, 8, 300))

@@ -11,7 +11,10 @@ namespace vcfb {
 
 static thread_local std::string g_err;
 
+static thread_local const char* g_kernel = "";
+
 void set_error(const std::string& msg) { g_err = msg; }
+void note_kernel(const char* name) { g_kernel = name; }
 
 int cuda_fail(cudaError_t e, const char* what) {
   g_err = std::string(what) + ": " + cudaGetErrorString(e);
@@ -55,6 +58,8 @@ int vcfb_version(void) { return VCFB_VERSION; }
 
 const char* vcfb_last_error(void) { return g_err.c_str(); }
 
+const char* vcfb_last_kernel(void) { return g_kernel; }
+
 int vcfb_device_count(void) {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) {
@@ -95,6 +100,8 @@ int vcfb_encode_dev(const uint8_t* rgb, int n_frames, int H, int W, int B, doubl
   a.flags = flags;
   a.weights = weights;
   a.stats = reinterpret_cast<unsigned long long*>(stats);
+  rc = launch_encode_fast(a, B, static_cast<cudaStream_t>(cuda_stream));
+  if (rc != VCFB_E_UNSUPP) return rc;
   return launch_encode_general(a, B, static_cast<cudaStream_t>(cuda_stream));
 }
 
@@ -117,6 +124,8 @@ int vcfb_decode_dev(const uint8_t* idx, int n_frames, int H, int W, int B, doubl
   a.flags = flags;
   a.weights = weights;
   a.stats = reinterpret_cast<unsigned long long*>(stats);
+  rc = launch_decode_fast(a, B, static_cast<cudaStream_t>(cuda_stream));
+  if (rc != VCFB_E_UNSUPP) return rc;
   return launch_decode_general(a, B, static_cast<cudaStream_t>(cuda_stream));
 }
 

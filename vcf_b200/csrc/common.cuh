@@ -48,9 +48,14 @@ struct DecArgs {
 
 void set_error(const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what);
+void note_kernel(const char* name);   // remembered per thread for vcfb_last_kernel()
 
 // general kernels (all B, float32 / float64): kernels_general.cu
 int launch_encode_general(const EncArgs& a, int B, cudaStream_t s);
 int launch_decode_general(const DecArgs& a, int B, cudaStream_t s);
+
+// fast path (kernels_fast.cu): VCFB_E_UNSUPP means "not covered, use the general kernel"
+int launch_encode_fast(const EncArgs& a, int B, cudaStream_t s);
+int launch_decode_fast(const DecArgs& a, int B, cudaStream_t s);
 
 }  // namespace vcfb

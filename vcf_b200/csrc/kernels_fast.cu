@@ -1,0 +1,682 @@
+// Fast path: B = 8, float32, YCoCg, subband layout -- the configuration BASELINE.json
+// quotes its metric on.  (Every other configuration runs the general kernels.)
+//
+// Design (DESIGN.md "fast path"):
+//   * persistent grid; every WARP is an autonomous pipeline over tiles of 8 rows x 128
+//     pixels (16 blocks): its own 3-deep ring of TMA loads and its own mbarriers, no
+//     CTA-wide barrier anywhere (only __syncwarp), so global memory is never
+//     touched by a thread: cp.async.bulk.tensor in, cp.async.bulk.tensor out;
+//   * zero padding of src/2D-DCT.py:216-227 is TMA's out-of-bounds fill (signed row
+//     coordinate = block row * 8 - top);
+//   * pass 1: a thread owns 4 adjacent pixel columns x 8 rows x 3 channels.  The
+//     colour transform is 3 dp4a per pixel on the packed bytes (exact integers
+//     4Y, 2Co, 4Cg of the centred pixel; the 1/4, 1/2 are lazy exponents), then 12
+//     pocketfft-exact length-8 DCTs in registers, written as float4 to an
+//     XOR-swizzled intermediate in shared memory;
+//   * pass 2: a thread owns one coefficient row u of 4 adjacent blocks x 3 channels:
+//     12 DCTs, one multiply per coefficient by a per-thread constant that folds all
+//     lazy power-of-two scales and 1/q (exact for power-of-two q; true division
+//     otherwise), truncation, bias + wrap, and 12 bytes per (u,i) go out as three
+//     32-bit words into the dense TMA store box [j][i][block*3+c];
+//   * every shared-memory offset is a compile-time immediate on a per-thread base.
+#include "common.cuh"
+#include "dct_codelets.cuh"
+#include "tma.cuh"
+
+#include <stdlib.h>
+
+namespace vcfb {
+
+namespace tma {
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+bool make_map(CUtensorMap* out, CUtensorMapDataType dt, int rank, void* base, const uint64_t* dims,
+              const uint64_t* strides_bytes, const uint32_t* box) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  cuuint64_t gd[5];
+  cuuint64_t gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i) gs[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = fn(out, dt, cuuint32_t(rank), base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+}  // namespace tma
+
+namespace {
+
+// ---- geometry of the warp-autonomous pipelines --------------------------------------
+constexpr int WT = 128;               // pixels per warp tile (16 blocks)
+constexpr int ROWW = WT * 3 / 4;      // 96 words per raw RGB row
+constexpr int TILE = 8 * WT * 3;      // 3072 bytes: raw tile == index tile
+constexpr int NSTAGE = 3;
+
+constexpr int ENC_FP = 132;           // floats per intermediate row (132 = 4 mod 32: conflict-free)
+constexpr int ENC_F_BYTES = 3 * 8 * ENC_FP * 4;
+constexpr int ENC_WARP_SMEM = 22016;  // ring 9216 + F 12672 + 3 mbarriers, rounded to 128
+
+template <typename T> struct DecL;
+// Intermediate X[c][y][i][16 blocks]: row pitch P and plane pitch PP (elements) are
+// chosen so that pass-1 stores (lanes = 8 values of i) and pass-2 loads (lanes = 4
+// block groups x 2 values of y) both touch 32 distinct banks per wavefront.
+template <> struct DecL<float> {
+  static constexpr int P = 20;              // 20 words = 4*odd  (mod 32)
+  static constexpr int PP = 8 * P + 16;     // 176 = 16 (mod 32): odd y lands on the other 16 banks
+  static constexpr int F_BYTES = 3 * 8 * PP * 4;
+  static constexpr int WARP_SMEM = 26240;
+};
+template <> struct DecL<double> {
+  static constexpr int P = 18;              // 36 words = 4*odd (mod 32)
+  static constexpr int PP = 8 * P + 2;      // 292 words = 4 (mod 8): odd y fills the gaps
+  static constexpr int F_BYTES = 3 * 8 * PP * 8;
+  static constexpr int WARP_SMEM = 37376;
+};
+static_assert(NSTAGE * TILE + ENC_F_BYTES + 8 * NSTAGE <= ENC_WARP_SMEM, "encode smem");
+static_assert(NSTAGE * TILE + DecL<float>::F_BYTES + 8 * NSTAGE <= DecL<float>::WARP_SMEM, "decode f32 smem");
+static_assert(NSTAGE * TILE + DecL<double>::F_BYTES + 8 * NSTAGE <= DecL<double>::WARP_SMEM, "decode f64 smem");
+
+struct FastArgs {
+  int ntiles, tiles_x, ny, top;
+  float q;
+  float qtab[8][3];   // [u][c]: sgn_u * 2^(exp_u + colour exp_c + min_i exp_i) (/ q when q is 2^k)
+};
+
+struct FastDecArgs {
+  int ntiles, tiles_x, ny, top;
+  int q;
+};
+
+__host__ __device__ constexpr double p2(int e) {
+  double r = 1.0;
+  for (int i = 0; i < (e < 0 ? -e : e); ++i) r = e < 0 ? r * 0.5 : r * 2.0;
+  return r;
+}
+
+using M8F = dct8_fwd_meta;
+using M8I = dct8_inv_meta;
+__host__ __device__ constexpr int min_exp8() {
+  int m = M8F::exp(0);
+  for (int i = 1; i < 8; ++i) m = M8F::exp(i) < m ? M8F::exp(i) : m;
+  return m;
+}
+__host__ __device__ constexpr bool inv8_uniform() {
+  for (int i = 0; i < 8; ++i)
+    if (M8I::exp(i) != M8I::exp(0) || M8I::sgn(i) != 1) return false;
+  return true;
+}
+static_assert(inv8_uniform(), "decode fast path assumes a uniform lazy scale of dct8_inv");
+
+__device__ __forceinline__ int dp4a_us(unsigned a, int b, int c) {
+  int d;
+  asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+
+constexpr int MAGIC_I = 0x4B400000;     // bits of 12582912.0f = 1.5 * 2^23
+constexpr float MAGIC_F = 12582912.0f;
+
+// (float) of the exact integer dot product of the pixel bytes with small signed
+// coefficients: the accumulator starts at the bit pattern of 1.5*2^23, so the dp4a
+// result *is* the float 1.5*2^23 + n; one subtraction removes the bias exactly.
+__device__ __forceinline__ float dotf(unsigned px, int coef, int bias) {
+  return __int_as_float(dp4a_us(px, coef, MAGIC_I + bias)) - MAGIC_F;
+}
+
+__device__ __forceinline__ unsigned pack4(int k0, int k1, int k2, int k3) {
+  const unsigned lo = __byte_perm(unsigned(k0), unsigned(k1), 0x0040);
+  const unsigned hi = __byte_perm(unsigned(k2), unsigned(k3), 0x0040);
+  return __byte_perm(lo, hi, 0x5410);
+}
+
+// Per-warp tile walker: which tiles this warp owns, and the TMA issue for them.
+struct Walker {
+  int tile, stride, ntiles, per_frame, tiles_x, top;
+  __device__ __forceinline__ void coords(int t, int& f, int& by, int& tx) const {
+    f = t / per_frame;
+    const int rem = t - f * per_frame;
+    by = rem / tiles_x;
+    tx = rem - by * tiles_x;
+  }
+};
+
+// ============================================================================
+// encode: one warp = one autonomous pipeline over tiles of 8 rows x 128 pixels
+// ============================================================================
+template <bool EXACT, bool QPOW2, int NWARPS, int CTAS>
+__global__ void __launch_bounds__(NWARPS * 32, CTAS)
+enc8_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
+                 const FastArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char* ring = smem + warp * ENC_WARP_SMEM;
+  float* F = reinterpret_cast<float*>(ring + NSTAGE * TILE);
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + NSTAGE * TILE + ENC_F_BYTES);
+
+  if (lane == 0) {
+    tma::prefetch_map(&in_map);
+    tma::prefetch_map(&out_map);
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) tma::mbar_init(&full[s], 1);
+    tma::fence_mbar_init();
+  }
+  __syncwarp();
+
+  Walker w;
+  w.tile = blockIdx.x * NWARPS + warp;
+  w.stride = gridDim.x * NWARPS;
+  w.ntiles = a.ntiles;
+  w.tiles_x = a.tiles_x;
+  w.per_frame = a.ny * a.tiles_x;
+  w.top = a.top;
+
+  auto issue_load = [&](int s, int t) {
+    int f, by, tx;
+    w.coords(t, f, by, tx);
+    tma::mbar_expect_tx(&full[s], TILE);
+    tma::load_3d(ring + s * TILE, &in_map, &full[s], tx * (WT * 3 / 8), by * 8 - w.top, f);
+  };
+  auto issue_store = [&](int s, int t) {
+    int f, by, tx;
+    w.coords(t, f, by, tx);
+    // out_map dims: (x bytes, j, block row, i, frame); smem box is [i][j][48 B]
+    tma::store_5d(&out_map, ring + s * TILE, tx * (WT / 8) * 3, 0, by, 0, f);
+    tma::commit_group();
+  };
+
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) {
+      const int t = w.tile + s * w.stride;
+      if (t < w.ntiles) issue_load(s, t);
+    }
+  }
+
+  // pass 1: lane = group of 4 pixel columns.  pass 2: lane = (coefficient row u, group of 4 blocks G)
+  const int u = lane & 7, G = lane >> 3;
+  float qs[3][2];   // [c][exp_i - min_exp]
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    qs[c][0] = a.qtab[u][c];
+    qs[c][1] = a.qtab[u][c] * 2.0f;
+  }
+  const float qf = a.q;
+
+  int k = 0;
+  for (int tile = w.tile; tile < w.ntiles; tile += w.stride, ++k) {
+    const int s = k % NSTAGE;
+    unsigned char* tb = ring + s * TILE;
+    tma::mbar_wait(&full[s], (k / NSTAGE) & 1);
+
+    // ---- pass 1: colour transform + DCT down the columns (axis 0) -------------------
+    {
+      float v[3][4][8];
+      const uint32_t* rw = reinterpret_cast<const uint32_t*>(tb) + 3 * lane;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const uint32_t w0 = rw[r * ROWW + 0];
+        const uint32_t w1 = rw[r * ROWW + 1];
+        const uint32_t w2 = rw[r * ROWW + 2];
+        const uint32_t p1 = __byte_perm(w0, w1, 0x0543);   // R1 G1 B1 .
+        const uint32_t p2v = __byte_perm(w1, w2, 0x0432);  // R2 G2 B2 .
+        // 4*Y = R + 2G + B - 512 ; 2*Co = R - B ; 4*Cg = -R + 2G - B   (centred pixel)
+        v[0][0][r] = dotf(w0, 0x00010201, -512);
+        v[1][0][r] = dotf(w0, 0x00FF0001, 0);
+        v[2][0][r] = dotf(w0, 0x00FF02FF, 0);
+        v[0][1][r] = dotf(p1, 0x00010201, -512);
+        v[1][1][r] = dotf(p1, 0x00FF0001, 0);
+        v[2][1][r] = dotf(p1, 0x00FF02FF, 0);
+        v[0][2][r] = dotf(p2v, 0x00010201, -512);
+        v[1][2][r] = dotf(p2v, 0x00FF0001, 0);
+        v[2][2][r] = dotf(p2v, 0x00FF02FF, 0);
+        v[0][3][r] = dotf(w2, 0x01020100, -512);            // . R3 G3 B3
+        v[1][3][r] = dotf(w2, int(0xFF000100), 0);
+        v[2][3][r] = dotf(w2, int(0xFF02FF00), 0);
+      }
+      float* fw = F + 4 * lane;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+#pragma unroll
+        for (int col = 0; col < 4; ++col) dct8_fwd<float, EXACT>(v[c][col]);
+#pragma unroll
+        for (int uu = 0; uu < 8; ++uu)
+          *reinterpret_cast<float4*>(fw + (c * 8 + uu) * ENC_FP) =
+              make_float4(v[c][0][uu], v[c][1][uu], v[c][2][uu], v[c][3][uu]);
+      }
+    }
+    __syncwarp();
+
+    // ---- pass 2: DCT along the rows (axis 1), quantise, pack -------------------------
+    {
+      float v[3][4][8];
+      const float* fr = F + u * ENC_FP + 32 * G;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          const float4 t4 = *reinterpret_cast<const float4*>(fr + c * 8 * ENC_FP + 4 * m);
+          v[c][m >> 1][(m & 1) * 4 + 0] = t4.x;
+          v[c][m >> 1][(m & 1) * 4 + 1] = t4.y;
+          v[c][m >> 1][(m & 1) * 4 + 2] = t4.z;
+          v[c][m >> 1][(m & 1) * 4 + 3] = t4.w;
+        }
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) dct8_fwd<float, EXACT>(v[c][b]);
+      // index box in smem: [i][j = u][16 blocks * 3 bytes]
+      uint32_t* ow = reinterpret_cast<uint32_t*>(tb) + u * 12 + 3 * G;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        int kk[4][3];
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float sc = M8F::sgn(i) > 0 ? qs[c][M8F::exp(i) - min_exp8()] : -qs[c][M8F::exp(i) - min_exp8()];
+            float t = __fmul_rn(v[c][b][i], sc);              // exact: sc is a power of two
+            if (!QPOW2) t = __fdiv_rn(t, qf);                 // src/deadzone.py:98  x / Q_step
+            kk[b][c] = __float2int_rz(t);                     // truncation = dead zone
+          }
+        uint32_t* o = ow + i * 96;
+        o[0] = pack4(kk[0][0], kk[0][1], kk[0][2], kk[1][0]) ^ 0x80808080u;   // +128, wraps
+        o[1] = pack4(kk[1][1], kk[1][2], kk[2][0], kk[2][1]) ^ 0x80808080u;
+        o[2] = pack4(kk[2][2], kk[3][0], kk[3][1], kk[3][2]) ^ 0x80808080u;
+      }
+    }
+    tma::fence_proxy_async();
+    __syncwarp();
+
+    if (lane == 0) {
+      issue_store(s, tile);
+      tma::wait_group_read<1>();          // the store issued one tile ago has drained its buffer
+      if (k >= 1) {
+        const int nt = tile + (NSTAGE - 1) * w.stride;
+        if (nt < w.ntiles) issue_load((k - 1) % NSTAGE, nt);
+      }
+    }
+    __syncwarp();
+  }
+  if (lane == 0) tma::wait_group<0>();
+}
+
+// ============================================================================
+// decode: same pipeline, inverse arithmetic.
+//
+//   index box [j][i][48 B]  ->  pass 1: lane = (coefficient column i, group of 4
+//   blocks G); per channel: dequantise 32 indices, 4 inverse DCTs over u (axis 0),
+//   X[c][y][i][block] written as 4 contiguous elements  ->  pass 2: lane = (pixel row
+//   y, G); inverse DCTs over i (axis 1), to_RGB, one fma for (lazy 2^-4, +128), clip +
+//   truncate, 96 bytes of RGB out  ->  TMA store of the 8 x 384-byte tile.
+//
+// T = double, EXACT = true is the reference's float64 chain operation for operation.
+// The double kernel keeps its channel / block-pair loops rolled so that the code stays
+// inside the instruction cache.
+// ============================================================================
+
+template <typename T> __device__ __forceinline__ T from_biased_int(unsigned biased);
+template <> __device__ __forceinline__ double from_biased_int<double>(unsigned biased) {
+  // 2^52 + 2^31 + k  minus  (2^52 + 2^31): both exact
+  return __dsub_rn(__hiloint2double(0x43300000, int(biased)), 4503601774854144.0);
+}
+template <> __device__ __forceinline__ float from_biased_int<float>(unsigned biased) {
+  return __int2float_rn(int(biased ^ 0x80000000u));
+}
+
+template <typename T> __device__ __forceinline__ int trunc_to_int(T x);
+template <> __device__ __forceinline__ int trunc_to_int<float>(float x) { return __float2int_rz(x); }
+template <> __device__ __forceinline__ int trunc_to_int<double>(double x) { return __double2int_rz(x); }
+
+__device__ __forceinline__ int clamp255(int v) { return min(max(v, 0), 255); }
+
+template <typename T> struct Vec;   // 16-byte vector of T
+template <> struct Vec<float> { using type = float4; static constexpr int N = 4; };
+template <> struct Vec<double> { using type = double2; static constexpr int N = 2; };
+
+template <typename T, bool EXACT, int NWARPS, int CTAS>
+__global__ void __launch_bounds__(NWARPS * 32, CTAS)
+dec8_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
+                 const FastDecArgs a) {
+  using O = Ops<T, EXACT>;
+  using L = DecL<T>;
+  constexpr int P = L::P;
+  constexpr bool F64 = sizeof(T) == 8;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char* ring = smem + warp * L::WARP_SMEM;
+  T* F = reinterpret_cast<T*>(ring + NSTAGE * TILE);
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + NSTAGE * TILE + L::F_BYTES);
+
+  if (lane == 0) {
+    tma::prefetch_map(&in_map);
+    tma::prefetch_map(&out_map);
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) tma::mbar_init(&full[s], 1);
+    tma::fence_mbar_init();
+  }
+  __syncwarp();
+
+  Walker w;
+  w.tile = blockIdx.x * NWARPS + warp;
+  w.stride = gridDim.x * NWARPS;
+  w.ntiles = a.ntiles;
+  w.tiles_x = a.tiles_x;
+  w.per_frame = a.ny * a.tiles_x;
+  w.top = a.top;
+  auto issue_load = [&](int s, int t) {
+    int f, by, tx;
+    w.coords(t, f, by, tx);
+    tma::mbar_expect_tx(&full[s], TILE);
+    // in_map dims: (x bytes, i, block row, j, frame); smem box is [j][i][48 B]
+    tma::load_5d(ring + s * TILE, &in_map, &full[s], tx * (WT / 8) * 3, 0, by, 0, f);
+  };
+  auto issue_store = [&](int s, int t) {
+    int f, by, tx;
+    w.coords(t, f, by, tx);
+    tma::store_3d(&out_map, ring + s * TILE, tx * (WT * 3 / 8), by * 8 - w.top, f);
+    tma::commit_group();
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) {
+      const int t = w.tile + s * w.stride;
+      if (t < w.ntiles) issue_load(s, t);
+    }
+  }
+
+  const int i1 = lane & 7, G1 = lane >> 3;     // pass 1: coefficient column i fastest
+  const int G2 = lane & 3, y2 = lane >> 2;     // pass 2: block group fastest
+  const int q = a.q;
+  const int qbias = int(0x80000000u) - 128 * q;      // byte*q + qbias = (byte-128)*q + 2^31
+  constexpr T SCALE = T(p2(2 * M8I::exp(0)));
+
+  int k = 0;
+  for (int tile = w.tile; tile < w.ntiles; tile += w.stride, ++k) {
+    const int s = k % NSTAGE;
+    unsigned char* tb = ring + s * TILE;
+    tma::mbar_wait(&full[s], (k / NSTAGE) & 1);
+
+    // ---- pass 1: dequantise + inverse DCT over u (axis 0) -------------------------
+    {
+      uint32_t wd[8][3];
+      const uint32_t* rw = reinterpret_cast<const uint32_t*>(tb) + i1 * 12 + 3 * G1;
+#pragma unroll
+      for (int uu = 0; uu < 8; ++uu) {
+        wd[uu][0] = rw[uu * 96 + 0];
+        wd[uu][1] = rw[uu * 96 + 1];
+        wd[uu][2] = rw[uu * 96 + 2];
+      }
+      T* fw = F + i1 * P + 4 * G1;
+#pragma unroll(F64 ? 1 : 3)
+      for (int c = 0; c < 3; ++c) {
+        T v[4][8];
+#pragma unroll
+        for (int uu = 0; uu < 8; ++uu) {
+          // bytes 3b + c of the 12-byte run, b = 0..3: shift the 96-bit run right by c bytes
+          const uint32_t s0 = __funnelshift_r(wd[uu][0], wd[uu][1], 8 * c);
+          const uint32_t s1 = __funnelshift_r(wd[uu][1], wd[uu][2], 8 * c);
+          const uint32_t s2 = wd[uu][2] >> (8 * c);
+          const int b0 = int(s0 & 255u), b1 = int(s0 >> 24), b2 = int((s1 >> 16) & 255u), b3 = int((s2 >> 8) & 255u);
+          // (byte - 128) * q: int16 * int of src/2D-DCT.py:398-410 (cannot wrap for q <= 255)
+          v[0][uu] = from_biased_int<T>(unsigned(b0 * q + qbias));
+          v[1][uu] = from_biased_int<T>(unsigned(b1 * q + qbias));
+          v[2][uu] = from_biased_int<T>(unsigned(b2 * q + qbias));
+          v[3][uu] = from_biased_int<T>(unsigned(b3 * q + qbias));
+        }
+#pragma unroll
+        for (int b = 0; b < 4; ++b) dct8_inv<T, EXACT>(v[b]);
+#pragma unroll
+        for (int yy = 0; yy < 8; ++yy) {
+          T* d = fw + (c * 8 + yy) * L::PP;
+          if (!F64) {
+            *reinterpret_cast<float4*>(d) = make_float4(float(v[0][yy]), float(v[1][yy]), float(v[2][yy]), float(v[3][yy]));
+          } else {
+            *reinterpret_cast<double2*>(d) = make_double2(double(v[0][yy]), double(v[1][yy]));
+            *reinterpret_cast<double2*>(d + 2) = make_double2(double(v[2][yy]), double(v[3][yy]));
+          }
+        }
+      }
+    }
+    __syncwarp();
+
+    // ---- pass 2: inverse DCT over i (axis 1), to_RGB, +128, clip, truncate -----------
+    {
+      constexpr int NB = F64 ? 2 : 4;            // blocks per step
+      const T* fr = F + y2 * L::PP + 4 * G2;
+      uint4* orow = reinterpret_cast<uint4*>(tb + y2 * (WT * 3) + 96 * G2);
+#pragma unroll(F64 ? 1 : 4)
+      for (int st = 0; st < 4 / NB; ++st) {
+        T v[3][NB][8];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const T* sp = fr + c * 8 * L::PP + i * P + NB * st;
+            if (!F64) {
+              const float4 t4 = *reinterpret_cast<const float4*>(sp);
+              v[c][0][i] = T(t4.x);
+              v[c][1][i] = T(t4.y);
+              v[c][NB - 2][i] = T(t4.z);
+              v[c][NB - 1][i] = T(t4.w);
+            } else {
+              const double2 t2 = *reinterpret_cast<const double2*>(sp);
+              v[c][0][i] = T(t2.x);
+              v[c][1][i] = T(t2.y);
+            }
+          }
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int b = 0; b < NB; ++b) dct8_inv<T, EXACT>(v[c][b]);
+        int px[NB][8][3];
+#pragma unroll
+        for (int b = 0; b < NB; ++b)
+#pragma unroll
+          for (int x = 0; x < 8; ++x) {
+            const T Y = v[0][b][x], Co = v[1][b][x], Cg = v[2][b][x];
+            // to_RGB: Y + Co - Cg ; Y + Cg ; Y - Co - Cg (left to right), then += 128;
+            // the lazy 2^-4 of the two codelets rides on the fma (exact product).
+            const T R = O::fma(O::sub(O::add(Y, Co), Cg), SCALE, T(128));
+            const T Gc = O::fma(O::add(Y, Cg), SCALE, T(128));
+            const T Bc = O::fma(O::sub(O::sub(Y, Co), Cg), SCALE, T(128));
+            px[b][x][0] = clamp255(trunc_to_int<T>(R));      // np.clip(y,0,255).astype(uint8)
+            px[b][x][1] = clamp255(trunc_to_int<T>(Gc));
+            px[b][x][2] = clamp255(trunc_to_int<T>(Bc));
+          }
+        // NB blocks x 8 px x 3 B = NB * 24 bytes
+        const int* p = &px[0][0][0];
+        uint32_t ww[NB * 6];
+#pragma unroll
+        for (int j = 0; j < NB * 6; ++j) ww[j] = pack4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
+#pragma unroll
+        for (int j = 0; j < NB * 6 / 4; ++j)
+          orow[(NB * 6 / 4) * st + j] = make_uint4(ww[4 * j], ww[4 * j + 1], ww[4 * j + 2], ww[4 * j + 3]);
+      }
+    }
+    tma::fence_proxy_async();
+    __syncwarp();
+
+    if (lane == 0) {
+      issue_store(s, tile);
+      tma::wait_group_read<1>();
+      if (k >= 1) {
+        const int nt = tile + (NSTAGE - 1) * w.stride;
+        if (nt < w.ntiles) issue_load((k - 1) % NSTAGE, nt);
+      }
+    }
+    __syncwarp();
+  }
+  if (lane == 0) tma::wait_group<0>();
+}
+
+// ---- host side -----------------------------------------------------------------
+
+bool fast_geometry_ok(const Geom& g, const void* p0, const void* p1) {
+  if (g.W % 16 != 0 || g.nx % 16 != 0 || g.left != 0) return false;
+  if ((reinterpret_cast<uintptr_t>(p0) & 15) || (reinterpret_cast<uintptr_t>(p1) & 15)) return false;
+  return tma::encode_tiled_fn() != nullptr;
+}
+
+// RGB frames as (W*3/8 uint64, H, n); box = one warp tile (48 uint64 x 8 rows)
+bool make_rgb_map(CUtensorMap* m, const Geom& g, int n, const void* base) {
+  const uint64_t dims[3] = {uint64_t(g.W) * 3 / 8, uint64_t(g.H), uint64_t(n)};
+  const uint64_t str[2] = {uint64_t(g.W) * 3, uint64_t(g.H) * g.W * 3};
+  const uint32_t box[3] = {WT * 3 / 8, 8, 1};
+  return tma::make_map(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void*>(base), dims, str, box);
+}
+
+// Index planes sub[j*ny + y, i*nx + x, c] as a 5-D tensor.  i_major=false: dims (x bytes,
+// i, y, j, frame) -> smem box [j][i][48]; i_major=true: dims (x bytes, j, y, i, frame)
+// -> smem box [i][j][48] (the order that makes the encoder's stores conflict-free).
+bool make_idx_map(CUtensorMap* m, const Geom& g, int n, const void* base, bool i_major) {
+  const uint64_t si = uint64_t(g.nx) * 3, sy = uint64_t(g.Wp) * 3, sj = uint64_t(g.ny) * g.Wp * 3,
+                 sf = uint64_t(g.Hp) * g.Wp * 3;
+  const uint64_t dims[5] = {uint64_t(g.nx) * 3, 8, uint64_t(g.ny), 8, uint64_t(n)};
+  const uint64_t str_j[4] = {si, sy, sj, sf};
+  const uint64_t str_i[4] = {sj, sy, si, sf};
+  const uint32_t box[5] = {WT / 8 * 3, 8, 1, 8, 1};
+  return tma::make_map(m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 5, const_cast<void*>(base), dims, i_major ? str_i : str_j,
+                       box);
+}
+
+int sm_count() {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms;
+}
+
+}  // namespace
+
+template <int NWARPS, int CTAS>
+static int launch_enc_t(bool exact, bool qpow2, const CUtensorMap& in_map, const CUtensorMap& out_map,
+                        const FastArgs& fa, cudaStream_t s) {
+  int grid = sm_count() * CTAS;
+  const int need = (fa.ntiles + NWARPS - 1) / NWARPS;
+  if (grid > need) grid = need;
+  void (*kern)(const CUtensorMap, const CUtensorMap, const FastArgs);
+  if (exact) kern = qpow2 ? enc8_fast_kernel<true, true, NWARPS, CTAS> : enc8_fast_kernel<true, false, NWARPS, CTAS>;
+  else kern = qpow2 ? enc8_fast_kernel<false, true, NWARPS, CTAS> : enc8_fast_kernel<false, false, NWARPS, CTAS>;
+  const int smem_bytes = NWARPS * ENC_WARP_SMEM;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(enc8_fast)");
+  note_kernel("enc8_fast");
+  kern<<<grid, NWARPS * 32, smem_bytes, s>>>(in_map, out_map, fa);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "enc8_fast_kernel launch");
+  return VCFB_OK;
+}
+
+// Returns VCFB_E_UNSUPP when the request is outside the fast path (the caller then
+// uses the general kernel), VCFB_OK after a launch, or an error.
+int launch_encode_fast(const EncArgs& a, int B, cudaStream_t s) {
+  if (B != 8 || a.color != VCFB_COLOR_YCOCG) return VCFB_E_UNSUPP;
+  if (a.flags & (VCFB_F_NO_SUBBANDS | VCFB_F_PERCEPTUAL | VCFB_F_FP64)) return VCFB_E_UNSUPP;
+  if (a.stats) return VCFB_E_UNSUPP;
+  const Geom& g = a.g;
+  if (!fast_geometry_ok(g, a.rgb, a.idx)) return VCFB_E_UNSUPP;
+  CUtensorMap in_map, out_map;
+  if (!make_rgb_map(&in_map, g, a.n_frames, a.rgb)) return VCFB_E_UNSUPP;
+  if (!make_idx_map(&out_map, g, a.n_frames, a.idx, true)) return VCFB_E_UNSUPP;
+
+  FastArgs fa;
+  fa.tiles_x = g.Wp / WT;
+  fa.ny = g.ny;
+  fa.top = g.top;
+  const long long nt = (long long)a.n_frames * g.ny * fa.tiles_x;
+  if (nt > 0x7fffffffLL - (1 << 20)) return VCFB_E_UNSUPP;
+  fa.ntiles = int(nt);
+  fa.q = float(a.q);
+  for (int u = 0; u < 8; ++u)
+    for (int c = 0; c < 3; ++c) {
+      const int cexp = (c == 1) ? -1 : -2;                  // 2*Co, 4*Y, 4*Cg
+      double sc = M8F::sgn(u) * p2(M8F::exp(u) + cexp + min_exp8());
+      if (a.q_pow2) sc *= a.inv_q;
+      fa.qtab[u][c] = float(sc);                             // a power of two: exact
+    }
+
+  const bool exact = !(a.flags & VCFB_F_CONTRACT);
+  // tuning knob (development only): VCFB_ENC_CFG = "<warps per CTA>x<CTAs per SM>"
+  int cfg = 42;
+  if (const char* e = getenv("VCFB_ENC_CFG")) cfg = (e[0] - '0') * 10 + (e[2] - '0');
+  switch (cfg) {
+    case 25: return launch_enc_t<2, 5>(exact, a.q_pow2, in_map, out_map, fa, s);
+    case 33: return launch_enc_t<3, 3>(exact, a.q_pow2, in_map, out_map, fa, s);
+    case 19: return launch_enc_t<1, 9>(exact, a.q_pow2, in_map, out_map, fa, s);
+    case 52: return launch_enc_t<5, 2>(exact, a.q_pow2, in_map, out_map, fa, s);
+    default: return launch_enc_t<4, 2>(exact, a.q_pow2, in_map, out_map, fa, s);
+  }
+}
+
+template <typename T, bool EXACT, int NWARPS, int CTAS>
+static int launch_dec_t(const CUtensorMap& in_map, const CUtensorMap& out_map, const FastDecArgs& fa, cudaStream_t s) {
+  using L = DecL<T>;
+  int grid = sm_count() * CTAS;
+  const int need = (fa.ntiles + NWARPS - 1) / NWARPS;
+  if (grid > need) grid = need;
+  auto kern = dec8_fast_kernel<T, EXACT, NWARPS, CTAS>;
+  const int smem_bytes = NWARPS * L::WARP_SMEM;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dec8_fast)");
+  note_kernel("dec8_fast");
+  kern<<<grid, NWARPS * 32, smem_bytes, s>>>(in_map, out_map, fa);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "dec8_fast_kernel launch");
+  return VCFB_OK;
+}
+
+int launch_decode_fast(const DecArgs& a, int B, cudaStream_t s) {
+  if (B != 8 || a.color != VCFB_COLOR_YCOCG) return VCFB_E_UNSUPP;
+  if (a.flags & (VCFB_F_NO_SUBBANDS | VCFB_F_PERCEPTUAL)) return VCFB_E_UNSUPP;
+  if (a.stats || a.original || a.y_out || !a.rgb) return VCFB_E_UNSUPP;
+  if (a.q_int < 1 || a.q_int > 255) return VCFB_E_UNSUPP;
+  const Geom& g = a.g;
+  // (a TMA store whose box starts at a negative row faults on sm_100a, so frames with
+  //  vertical padding take the general kernel)
+  if (!fast_geometry_ok(g, a.rgb, a.idx) || g.top != 0) return VCFB_E_UNSUPP;
+  CUtensorMap in_map, out_map;
+  if (!make_idx_map(&in_map, g, a.n_frames, a.idx, false)) return VCFB_E_UNSUPP;
+  if (!make_rgb_map(&out_map, g, a.n_frames, a.rgb)) return VCFB_E_UNSUPP;
+  FastDecArgs fa;
+  fa.tiles_x = g.Wp / WT;
+  fa.ny = g.ny;
+  fa.top = g.top;
+  const long long nt = (long long)a.n_frames * g.ny * fa.tiles_x;
+  if (nt > 0x7fffffffLL - (1 << 20)) return VCFB_E_UNSUPP;
+  fa.ntiles = int(nt);
+  fa.q = a.q_int;
+  int cfg = 0;   // tuning knob (development only): VCFB_DEC_CFG = "<warps per CTA>x<CTAs per SM>"
+  if (const char* e = getenv("VCFB_DEC_CFG")) cfg = (e[0] - '0') * 10 + (e[2] - '0');
+  if (a.flags & VCFB_F_FP64) {
+    switch (cfg) {
+      case 16: return launch_dec_t<double, true, 1, 6>(in_map, out_map, fa, s);
+      case 32: return launch_dec_t<double, true, 3, 2>(in_map, out_map, fa, s);
+      case 23: return launch_dec_t<double, true, 2, 3>(in_map, out_map, fa, s);
+      default: return launch_dec_t<double, true, 4, 1>(in_map, out_map, fa, s);
+    }
+  }
+  if (a.flags & VCFB_F_CONTRACT) return launch_dec_t<float, false, 4, 2>(in_map, out_map, fa, s);
+  return launch_dec_t<float, true, 4, 2>(in_map, out_map, fa, s);
+}
+
+}  // namespace vcfb

@@ -535,6 +535,7 @@ int launch_enc(const EncArgs& a, cudaStream_t s) {
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::ENC_SMEM);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(encode)");
   dim3 grid((a.g.Wp + L::TW - 1) / L::TW, a.g.ny, a.n_frames);
+  note_kernel("encode_general");
   kern<<<grid, NT, L::ENC_SMEM, s>>>(a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "encode_kernel launch");
@@ -548,6 +549,7 @@ int launch_dec(const DecArgs& a, cudaStream_t s) {
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DEC_SMEM);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(decode)");
   dim3 grid((a.g.Wp + L::TW - 1) / L::TW, a.g.ny, a.n_frames);
+  note_kernel("decode_general");
   kern<<<grid, NT, L::DEC_SMEM, s>>>(a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "decode_kernel launch");
