@@ -59,54 +59,58 @@ def parse():
 # clocks
 # ----------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons during the timed region, polled through NVML
+    every few milliseconds (the timed region is tens of milliseconds long)."""
 
     def __init__(self, gpu_index: int):
-        self.rows = []
-        self.proc = None
         self.idx = gpu_index
+        self.samples = []
+        self.stop_flag = threading.Event()
+        self.ok = False
+        self.mx = None
+        try:
+            import pynvml
+            self.nv = pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and vis.split(",")[gpu_index].isdigit() else gpu_index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                clk = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                self.samples.append((time.time(), float(clk), int(rs)))
+            except Exception:
+                pass
+            time.sleep(0.003)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
-                 "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._pump, daemon=True)
+        if self.ok:
+            self.t = threading.Thread(target=self._loop, daemon=True)
             self.t.start()
-        except Exception:
-            self.proc = None
-
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
 
     def stop(self, t0, t1):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], None, set()
-        for ts, line in self.rows:
-            p = [x.strip() for x in line.split(",")]
-            if len(p) < 8:
-                continue
-            try:
-                mx = float(p[2])
-                if t0 <= ts <= t1 + 0.15:
-                    sm.append(float(p[1]))
-                    for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), p[4:8]):
-                        if v.lower().startswith("active"):
-                            reasons.add(name)
-            except ValueError:
-                continue
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "samples": len(sm),
-                "reasons": sorted(reasons)}
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["nvml unavailable"]}
+        self.stop_flag.set()
+        self.t.join(timeout=1)
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+        inside = [x for x in self.samples if t0 <= x[0] <= t1]
+        sm = sorted(x[1] for x in inside)
+        reasons = sorted(n for n, bit in names.items() if any(x[2] & bit for x in inside))
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None,
+                "sm_max_mhz": self.mx, "samples": len(sm), "reasons": reasons}
 
 
 # ----------------------------------------------------------------------------
@@ -232,6 +236,7 @@ def run_ours(a):
     import torch
     import torch.distributed as dist
     from vcf_b200 import Codec, _lib
+    from vcf_b200.frames import allreduce_stats
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -253,25 +258,27 @@ def run_ours(a):
     y = torch.empty((n, H, W, 3), dtype=torch.uint8, device=dev)
     rde = a.workload == "rde"
     launches = 0
+    kernels_seen = {}
 
     def step(s, ev=None):
         nonlocal launches
         q = QS[s % 4]
         if ev:
             ev[0].record()
+        kn = kernels_seen
         if rde:
             _, st_e = enc[q].encode(x, out=idx, stats=True)
         else:
             enc[q].encode(x, out=idx)
+        kn["encode"] = _lib.last_kernel()
         if ev:
             ev[1].record()
         if rde:
             r = dec[q].decode(idx, (H, W), out=y, original=x, stats=True)
-            st = r[-1] + st_e
-            if world > 1:
-                dist.all_reduce(st)
+            st = allreduce_stats(r[-1] + st_e)      # one NCCL all-reduce of int64[776] per batch
         else:
             dec[q].decode(idx, (H, W), out=y)
+        kn["decode"] = _lib.last_kernel()
         if ev:
             ev[2].record()
         launches += 2
@@ -288,7 +295,7 @@ def run_ours(a):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)
+        time.sleep(0.05)
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(a.steps)]
     launches = 0
     barrier()
@@ -368,7 +375,7 @@ def run_ours(a):
             traffic = json.load(open(tpath)).get(dom)
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": f"{dom}_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": f"{kernels_seen.get(dom)} ({dom})", "kernels": kernels_seen, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "alg_bytes_per_launch": (ALG_BYTES_PER_PX[dom] + extra_b) * px_step,
                 "encode_ms_per_launch": enc_ms, "decode_ms_per_launch": dec_ms,

@@ -70,7 +70,9 @@ extern "C" {
 #define VCFB_STAT_NONZERO 4    /* indices != 0 after removing the 128 bias */
 #define VCFB_STAT_SUMABS 5     /* sum |index| */
 #define VCFB_STAT_NINDICES 6   /* indices written (Hp*Wp*3 per frame) */
-#define VCFB_STAT_RESERVED 7
+#define VCFB_STAT_SUMDIFF 7    /* signed sum (original - decoded): lets a caller form
+                                  sum((original - c) - decoded)^2 for any constant c, which is
+                                  what src/2D-DCT.py:572-574 compares (image still shifted by 128) */
 #define VCFB_STAT_HIST 8       /* 3 x 256 histogram of the uint8 indices, channel-major */
 #define VCFB_STAT_LEN (8 + 3 * 256)
 

@@ -168,6 +168,7 @@ def test_float_output_and_stats(torch_cuda):
     for c in range(3):
         assert int(st["sse"][c]) == O.sse_int(img[..., c], rgb[..., c])
     assert st["nsamples"] == img.size
+    assert st["sumdiff"] == int((img.astype(np.int64) - rgb.astype(np.int64)).sum())
     assert abs(st["rmse"] - float(O.rmse(img, rgb))) < 1e-4
     got, se = _codec(block_size=B, q=q).encode(img, stats=True)
     nz, sabs, hist = O.index_stats(got)

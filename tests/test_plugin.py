@@ -1,0 +1,142 @@
+"""The drop-in spatial-transform module (vcf_b200/plugin/2D-DCT-B200.py) driven through a
+CoDec chain, exactly as the reference drives src/2D-DCT.py: CLI, flags, side files."""
+import io
+import os
+import struct
+import subprocess
+import sys
+
+import cv2
+import numpy as np
+import pytest
+
+from oracle import vcf_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+STUB = os.path.join(ROOT, "tests", "vcf_stub")
+PLUGIN_DIR = os.path.join(ROOT, "vcf_b200", "plugin")
+PLUGIN = os.path.join(PLUGIN_DIR, "2D-DCT-B200.py")
+REF_SRC = "/root/reference/src"
+
+
+def _run(cwd, script, *argv, extra_path=()):
+    env = dict(os.environ)
+    env["PYTHONPATH"] = os.pathsep.join([PLUGIN_DIR, ROOT, *extra_path, env.get("PYTHONPATH", "")])
+    env["PYTHONDONTWRITEBYTECODE"] = "1"
+    return subprocess.run([sys.executable, script, *argv], cwd=cwd, env=env, capture_output=True, text=True)
+
+
+def _write_png(fn, img):
+    assert cv2.imwrite(fn, cv2.cvtColor(img, cv2.COLOR_RGB2BGR))
+
+
+def _read_png(fn):
+    return cv2.cvtColor(cv2.imread(fn, cv2.IMREAD_UNCHANGED), cv2.COLOR_BGR2RGB)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("flags,kw", [
+    ([], dict(B=8, q=32)),
+    (["-B", "16", "-q", "8"], dict(B=16, q=8)),
+    (["-q", "12", "-x"], dict(B=8, q=12, disable_subbands=True)),
+    (["-q", "4", "-p"], dict(B=8, q=4, perceptual=True)),
+    (["-t", "YCrCb"], dict(B=8, q=32)),     # -t only changes the base class (src/2D-DCT.py:22-23)
+])
+def test_cli_encode_decode_matches_reference_semantics(flags, kw):
+    img = O.synthetic_frame(136, 200, 31, "natural")       # 136 = 17*8: padding for B=16
+    _write_png("/tmp/original.png", img)
+    for f in ("/tmp/encoded.npz", "/tmp/encoded_shape.bin", "/tmp/decoded.png"):
+        if os.path.exists(f):
+            os.remove(f)
+    r = _run(STUB, PLUGIN, "encode", *flags)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert struct.unpack("iii", open("/tmp/encoded_shape.bin", "rb").read()) == img.shape
+    idx = np.load("/tmp/encoded.npz")["a"]
+    assert np.array_equal(idx, O.encode_array(img, **kw))
+    r = _run(STUB, PLUGIN, "decode", *flags)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert np.array_equal(_read_png("/tmp/decoded.png"), O.decode_array(idx, img.shape, **kw))
+
+
+@pytest.mark.gpu
+def test_cli_post_filter_gets_unclipped_float():
+    img = O.synthetic_frame(64, 128, 32, "natural")
+    _write_png("/tmp/original.png", img)
+    assert _run(STUB, PLUGIN, "encode", "-q", "16").returncode == 0
+    r = _run(STUB, PLUGIN, "decode", "-q", "16", "-f", "half_filter")
+    assert r.returncode == 0, r.stderr[-2000:]
+    idx = np.load("/tmp/encoded.npz")["a"]
+    yf = O.decode_array(idx, img.shape, 8, 16, return_float=True)
+    want = np.clip(yf * 0.5 + 300.25, 0, 255).astype(np.uint8)
+    assert np.array_equal(_read_png("/tmp/decoded.png"), want)
+
+
+@pytest.mark.gpu
+def test_iii_style_per_frame_loop_and_block_size_optimiser():
+    frames = [O.synthetic_frame(64, 128, 60 + i, "natural") for i in range(3)]
+    for i, f in enumerate(frames):
+        _write_png("/tmp/original_%04d.png" % i, f)
+    r = _run(STUB, "III_stub.py", "encode", "-N", "3", "-q", "16")
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = _run(STUB, "III_stub.py", "decode", "-N", "3", "-q", "16")
+    assert r.returncode == 0, r.stderr[-2000:]
+    for i, f in enumerate(frames):
+        idx = np.load("/tmp/encoded_%04d.npz" % i)["a"]
+        assert np.array_equal(idx, O.encode_array(f, 8, 16))
+        assert np.array_equal(_read_png("/tmp/decoded_%04d.png" % i), O.decode_array(idx, f.shape, 8, 16))
+    # -L: J = rate + Lambda*RMSE over the supported block sizes (src/2D-DCT.py:533-579)
+    img = frames[0]
+    _write_png("/tmp/original.png", img)
+    r = _run(STUB, PLUGIN, "encode", "-L", "50.0", "-q", "16", "-g")
+    assert r.returncode == 0, r.stderr[-2000:]
+    best, bestJ = None, 1e18
+    for B in (4, 8, 16, 32):
+        k = O.encode_array(img, B, 16)
+        b = io.BytesIO()
+        np.savez_compressed(file=b, a=k)
+        y = O.decode_array(k, img.shape, B, 16)
+        rm = float(np.sqrt(np.mean(((img.astype(np.float64) - 128) - y) ** 2)))
+        J = len(b.getvalue()) + 50.0 * rm
+        if J < bestJ:
+            best, bestJ = B, J
+    assert f"optimal block_size={best}" in r.stderr, r.stderr[-1500:]
+    assert np.array_equal(np.load("/tmp/encoded.npz")["a"], O.encode_array(img, best, 16))
+
+
+def test_plugin_registers_reference_flags_without_gpu():
+    """No GPU needed: import-time behaviour, flag names / dests and class chain."""
+    r = _run(STUB, PLUGIN, "encode", "-h")
+    assert r.returncode == 0, r.stderr[-1500:]
+    for flag in ("--block_size_DCT", "--color_transform", "--perceptual_quantization", "--disable_subbands",
+                 "--Lambda"):
+        assert flag in r.stdout
+    r = _run(STUB, PLUGIN, "decode", "-h")
+    for flag in ("--block_size_DCT", "--color_transform", "--perceptual_quantization", "--disable_subbands"):
+        assert flag in r.stdout
+    code = ("import importlib, sys; sys.argv=['x','decode','-B','16','-q','8'];"
+            "m = importlib.import_module('2D-DCT-B200'); import parser; c = m.CoDec(parser.parser.parse_known_args()[0]);"
+            "print([k.__module__ for k in type(c).__mro__][:6], c.block_size, c.QSS, c.offset)")
+    r = _run(STUB, "-c", code)
+    assert r.returncode == 0, r.stderr[-1500:]
+    assert "'2D-DCT-B200', 'YCoCg', 'deadzone', 'no_filter', 'z_lib', 'entropy_image_coding'" in r.stdout
+    assert r.stdout.strip().endswith("16 8 128")
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SRC), reason="reference only present in the build container")
+def test_plugin_against_the_real_reference_chain_cpu():
+    """With the reference's own main/parser/YCoCg/deadzone/no_filter/z_lib modules (and the
+    shadow packages for its four external imports): same MRO as src/2D-DCT.py, and the
+    arithmetic refuses to run without a GPU instead of falling back."""
+    shims = os.path.join(ROOT, "oracle", "shims")
+    code = ("import importlib, sys; sys.argv=['x','encode','-c','z_lib'];"
+            "m = importlib.import_module('2D-DCT-B200'); import parser; c = m.CoDec(parser.parser.parse_known_args()[0]);"
+            "print([k.__module__ for k in type(c).__mro__][:6])")
+    r = _run(REF_SRC, "-c", code, extra_path=(shims,))
+    assert r.returncode == 0, r.stderr[-1500:]
+    assert "'2D-DCT-B200', 'YCoCg', 'deadzone', 'no_filter', 'z_lib', 'entropy_image_coding'" in r.stdout
+    from vcf_b200 import _lib
+    if _lib.lib().vcfb_device_count() == 0:
+        img = O.synthetic_frame(16, 16, 1, "noise")
+        _write_png("/tmp/original.png", img)
+        r = _run(REF_SRC, PLUGIN, "encode", "-c", "z_lib", extra_path=(shims,))
+        assert r.returncode != 0 and "no CPU fallback" in r.stderr

@@ -1,0 +1,16 @@
+'''A non-identity decoding filter for tests: operates on the FLOAT image it receives.'''
+import importlib
+with open("/tmp/description.txt", 'w') as f:
+    f.write(__doc__)
+import parser
+
+parser.parser_encode.add_argument("-c", "--entropy_image_codec", default="z_lib")
+parser.parser_decode.add_argument("-c", "--entropy_image_codec", default="z_lib")
+args = parser.parser.parse_known_args()[0]
+EC = importlib.import_module(args.entropy_image_codec)
+
+
+class CoDec(EC.CoDec):
+    def filter(self, img):
+        assert img.dtype.kind == "f", "post-filters get the un-clipped float image"
+        return img * 0.5 + 300.25

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvcfb200.so")
 
 STAT_SSE_R, STAT_SSE_G, STAT_SSE_B, STAT_NSAMPLES = 0, 1, 2, 3
-STAT_NONZERO, STAT_SUMABS, STAT_NINDICES, STAT_HIST = 4, 5, 6, 8
+STAT_NONZERO, STAT_SUMABS, STAT_NINDICES, STAT_SUMDIFF, STAT_HIST = 4, 5, 6, 7, 8
 STAT_LEN = 8 + 3 * 256
 
 COLOR_YCOCG, COLOR_YCRCB = 0, 1

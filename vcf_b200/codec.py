@@ -59,7 +59,8 @@ def stats_dict(vec: np.ndarray) -> dict:
     sse = v[0:3].copy()
     n = int(v[3])
     hist = v[STAT_HIST:STAT_HIST + 768].reshape(3, 256).copy()
-    out = dict(sse=sse, nsamples=n, nonzero=int(v[4]), sumabs=int(v[5]), nindices=int(v[6]), hist=hist)
+    out = dict(sse=sse, nsamples=n, nonzero=int(v[4]), sumabs=int(v[5]), nindices=int(v[6]),
+               sumdiff=int(v[7]), hist=hist)
     if n:
         mse = float(sse.sum()) / n
         out["mse"] = mse

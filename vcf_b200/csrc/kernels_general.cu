@@ -476,6 +476,7 @@ __global__ void __launch_bounds__(NT) decode_kernel(const DecArgs a) {
   // ---- store rows, SSE against the original (src/RDE.py:41-49) -----------------
   {
     unsigned sse[3] = {0, 0, 0};
+    int sdiff = 0;
     const bool do_sse = a.stats != nullptr && a.original != nullptr;
     constexpr int CH = OUTP / 16;
     if (outlen > 0) {
@@ -502,6 +503,7 @@ __global__ void __launch_bounds__(NT) decode_kernel(const DecArgs a) {
           for (int b = vlo; b < vhi; ++b) {
             const int d = int(op[b]) - int(sp[b]);
             sse[(b - sh) % 3] += unsigned(d * d);
+            sdiff += d;
           }
         }
       }
@@ -512,8 +514,13 @@ __global__ void __launch_bounds__(NT) decode_kernel(const DecArgs a) {
         const unsigned s = warp_sum(sse[c]);
         if ((tid & 31) == 0 && s) atomicAdd(&ssse[c], (unsigned long long)s);
       }
+      {
+        const unsigned sd = warp_sum(unsigned(sdiff));           // two's complement sum
+        if ((tid & 31) == 0 && sd) atomicAdd(&ssse[3], (unsigned long long)(long long)(int)sd);
+      }
       __syncthreads();
       if (tid < 3 && ssse[tid]) atomicAdd(a.stats + VCFB_STAT_SSE_R + tid, ssse[tid]);
+      if (tid == 4 && ssse[3]) atomicAdd(a.stats + VCFB_STAT_SUMDIFF, ssse[3]);
       if (tid == 3) {
         int rows = 0;
         for (int r = 0; r < B; ++r) {
