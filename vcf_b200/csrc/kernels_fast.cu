@@ -529,6 +529,175 @@ dec8_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_consta
   if (lane == 0) tma::wait_group<0>();
 }
 
+// ---- float64 decode, half-tile variant ------------------------------------------------
+// Same pipeline, but the 16-block tile is processed as two halves of 8 blocks so that the
+// float64 intermediate is 16.9 KB instead of 28 KB per warp: 8 warps per SM (two per
+// scheduler) instead of 4, which is what keeps the FP64 pipe fed.  Lane mapping: pass 1 =
+// (coefficient column i, pair of blocks), pass 2 = (pixel row y, pair of blocks).  The index
+// words of both halves are read into registers before the first half's RGB bytes overwrite
+// the (aliased) tile buffer.
+constexpr int H64_P = 10;                // doubles per (y,i) row of 8 blocks: 20 words = 4*odd
+constexpr int H64_PP = 8 * H64_P + 8;    // 88 doubles: odd y lands on the other 16 banks
+constexpr int H64_F_BYTES = 3 * 8 * H64_PP * 8;
+constexpr int H64_WARP_SMEM = 26240;
+static_assert(NSTAGE * TILE + H64_F_BYTES + 8 * NSTAGE <= H64_WARP_SMEM, "decode f64 half-tile smem");
+
+template <bool EXACT, int NWARPS, int CTAS>
+__global__ void __launch_bounds__(NWARPS * 32, CTAS)
+dec8_f64h_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
+                 const FastDecArgs a) {
+  using T = double;
+  using O = Ops<double, EXACT>;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char* ring = smem + warp * H64_WARP_SMEM;
+  T* F = reinterpret_cast<T*>(ring + NSTAGE * TILE);
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + NSTAGE * TILE + H64_F_BYTES);
+
+  if (lane == 0) {
+    tma::prefetch_map(&in_map);
+    tma::prefetch_map(&out_map);
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) tma::mbar_init(&full[s], 1);
+    tma::fence_mbar_init();
+  }
+  __syncwarp();
+
+  Walker w;
+  w.tile = blockIdx.x * NWARPS + warp;
+  w.stride = gridDim.x * NWARPS;
+  w.ntiles = a.ntiles;
+  w.tiles_x = a.tiles_x;
+  w.per_frame = a.ny * a.tiles_x;
+  w.top = a.top;
+  auto issue_load = [&](int s, int t) {
+    int f, by, tx;
+    w.coords(t, f, by, tx);
+    tma::mbar_expect_tx(&full[s], TILE);
+    tma::load_5d(ring + s * TILE, &in_map, &full[s], tx * (WT / 8) * 3, 0, by, 0, f);
+  };
+  auto issue_store = [&](int s, int t) {
+    int f, by, tx;
+    w.coords(t, f, by, tx);
+    tma::store_3d(&out_map, ring + s * TILE, tx * (WT * 3 / 8), by * 8 - w.top, f);
+    tma::commit_group();
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < NSTAGE; ++s) {
+      const int t = w.tile + s * w.stride;
+      if (t < w.ntiles) issue_load(s, t);
+    }
+  }
+
+  const int i1 = lane & 7, G1 = lane >> 3;     // pass 1
+  const int G2 = lane & 3, y2 = lane >> 2;     // pass 2
+  const int q = a.q;
+  const int qbias = int(0x80000000u) - 128 * q;
+  const int woff = (6 * G1) >> 2;              // word of the first byte of the lane's 6-byte run
+  const int sh0 = ((6 * G1) & 3) * 8;          // bit offset inside that word (0 or 16)
+  constexpr T SCALE = T(p2(2 * M8I::exp(0)));
+
+  int k = 0;
+  for (int tile = w.tile; tile < w.ntiles; tile += w.stride, ++k) {
+    const int s = k % NSTAGE;
+    unsigned char* tb = ring + s * TILE;
+    tma::mbar_wait(&full[s], (k / NSTAGE) & 1);
+
+    uint32_t wd[2][8][2];
+    {
+      const uint32_t* rw = reinterpret_cast<const uint32_t*>(tb) + i1 * 12 + woff;
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int uu = 0; uu < 8; ++uu) {
+          wd[h][uu][0] = rw[uu * 96 + 6 * h];
+          wd[h][uu][1] = rw[uu * 96 + 6 * h + 1];
+        }
+    }
+    __syncwarp();
+
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      // ---- pass 1: dequantise + inverse DCT over u, 2 blocks per lane and channel ------
+      {
+        T* fw = F + i1 * H64_P + 2 * G1;
+#pragma unroll 1
+        for (int c = 0; c < 3; ++c) {
+          T v[2][8];
+#pragma unroll
+          for (int uu = 0; uu < 8; ++uu) {
+            const uint32_t sv = __funnelshift_rc(wd[h][uu][0], wd[h][uu][1], sh0 + 8 * c);
+            // (byte - 128) * q: int16 * int of src/2D-DCT.py:398-410 (cannot wrap for q <= 255);
+            // the int -> double conversion is exact and runs off the FP64 pipe
+            v[0][uu] = __int2double_rn(int(sv & 255u) * q - 128 * q);
+            v[1][uu] = __int2double_rn(int(sv >> 24) * q - 128 * q);
+          }
+          dct8_inv<T, EXACT>(v[0]);
+          dct8_inv<T, EXACT>(v[1]);
+#pragma unroll
+          for (int yy = 0; yy < 8; ++yy)
+            *reinterpret_cast<double2*>(fw + (c * 8 + yy) * H64_PP) = make_double2(v[0][yy], v[1][yy]);
+        }
+      }
+      __syncwarp();
+      // ---- pass 2: inverse DCT over i, to_RGB, +128, clip, truncate ----------------------
+      {
+        const T* fr = F + y2 * H64_PP + 2 * G2;
+        T v[3][2][8];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const double2 t2 = *reinterpret_cast<const double2*>(fr + c * 8 * H64_PP + i * H64_P);
+            v[c][0][i] = t2.x;
+            v[c][1][i] = t2.y;
+          }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          dct8_inv<T, EXACT>(v[c][0]);
+          dct8_inv<T, EXACT>(v[c][1]);
+        }
+        int px[2][8][3];
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+          for (int x = 0; x < 8; ++x) {
+            const T Y = v[0][b][x], Co = v[1][b][x], Cg = v[2][b][x];
+            const T R = O::fma(O::sub(O::add(Y, Co), Cg), SCALE, T(128));
+            const T Gc = O::fma(O::add(Y, Cg), SCALE, T(128));
+            const T Bc = O::fma(O::sub(O::sub(Y, Co), Cg), SCALE, T(128));
+            px[b][x][0] = clamp255(__double2int_rz(R));
+            px[b][x][1] = clamp255(__double2int_rz(Gc));
+            px[b][x][2] = clamp255(__double2int_rz(Bc));
+          }
+        const int* p = &px[0][0][0];
+        uint32_t ww[12];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) ww[j] = pack4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]);
+        uint4* orow = reinterpret_cast<uint4*>(tb + y2 * (WT * 3) + 192 * h + 48 * G2);
+        orow[0] = make_uint4(ww[0], ww[1], ww[2], ww[3]);
+        orow[1] = make_uint4(ww[4], ww[5], ww[6], ww[7]);
+        orow[2] = make_uint4(ww[8], ww[9], ww[10], ww[11]);
+      }
+      __syncwarp();
+    }
+    tma::fence_proxy_async();
+    __syncwarp();
+
+    if (lane == 0) {
+      issue_store(s, tile);
+      tma::wait_group_read<1>();
+      if (k >= 1) {
+        const int nt = tile + (NSTAGE - 1) * w.stride;
+        if (nt < w.ntiles) issue_load((k - 1) % NSTAGE, nt);
+      }
+    }
+    __syncwarp();
+  }
+  if (lane == 0) tma::wait_group<0>();
+}
+
 // ---- host side -----------------------------------------------------------------
 
 bool fast_geometry_ok(const Geom& g, const void* p0, const void* p1) {
@@ -645,6 +814,23 @@ static int launch_dec_t(const CUtensorMap& in_map, const CUtensorMap& out_map, c
   return VCFB_OK;
 }
 
+template <int NWARPS, int CTAS>
+static int launch_dec_f64h(const CUtensorMap& in_map, const CUtensorMap& out_map, const FastDecArgs& fa,
+                           cudaStream_t s) {
+  int grid = sm_count() * CTAS;
+  const int need = (fa.ntiles + NWARPS - 1) / NWARPS;
+  if (grid > need) grid = need;
+  auto kern = dec8_f64h_kernel<true, NWARPS, CTAS>;
+  const int smem_bytes = NWARPS * H64_WARP_SMEM;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dec8_f64h)");
+  note_kernel("dec8_fast");
+  kern<<<grid, NWARPS * 32, smem_bytes, s>>>(in_map, out_map, fa);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "dec8_f64h_kernel launch");
+  return VCFB_OK;
+}
+
 int launch_decode_fast(const DecArgs& a, int B, cudaStream_t s) {
   if (B != 8 || a.color != VCFB_COLOR_YCOCG) return VCFB_E_UNSUPP;
   if (a.flags & (VCFB_F_NO_SUBBANDS | VCFB_F_PERCEPTUAL)) return VCFB_E_UNSUPP;
@@ -672,7 +858,9 @@ int launch_decode_fast(const DecArgs& a, int B, cudaStream_t s) {
       case 16: return launch_dec_t<double, true, 1, 6>(in_map, out_map, fa, s);
       case 32: return launch_dec_t<double, true, 3, 2>(in_map, out_map, fa, s);
       case 23: return launch_dec_t<double, true, 2, 3>(in_map, out_map, fa, s);
-      default: return launch_dec_t<double, true, 4, 1>(in_map, out_map, fa, s);
+      case 41: return launch_dec_t<double, true, 4, 1>(in_map, out_map, fa, s);
+      case 42: return launch_dec_f64h<4, 2>(in_map, out_map, fa, s);
+      default: return launch_dec_f64h<8, 1>(in_map, out_map, fa, s);
     }
   }
   if (a.flags & VCFB_F_CONTRACT) return launch_dec_t<float, false, 4, 2>(in_map, out_map, fa, s);
