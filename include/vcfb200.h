@@ -121,6 +121,20 @@ int vcfb_decode_dev(const uint8_t* idx, int n_frames, int H, int W, int B, doubl
                     uint8_t* rgb_out, void* y_out, const uint8_t* original,
                     int64_t* stats, void* cuda_stream);
 
+/* Stand-alone colour codecs: the reference's colour stages run as codecs of their own
+ * (`python YCoCg.py encode`, `python YCrCb.py encode`), colour transform + deadzone
+ * quantiser without a spatial transform.
+ *   encode replaces src/YCoCg.py:36-52 (color = VCFB_COLOR_YCOCG: astype(int16), from_RGB
+ *          stored into int16, x / q truncated, astype(uint16)) or src/YCrCb.py:36-47
+ *          (VCFB_COLOR_YCRCB: OpenCV 8-bit fixed-point RGB2YCrCb, then the same quantiser);
+ *   decode replaces src/YCoCg.py:61-78 / src/YCrCb.py:56-66 (note the uint8 cast before
+ *          to_RGB at :59).
+ * rgb: n_pixels x 3 uint8; k: n_pixels x 3 uint16; device pointers. */
+int vcfb_color_encode_dev(const uint8_t* rgb, long long n_pixels, double q, int color,
+                          uint16_t* k_out, void* cuda_stream);
+int vcfb_color_decode_dev(const uint16_t* k, long long n_pixels, double q, int color,
+                          uint8_t* rgb_out, void* cuda_stream);
+
 /* Host-buffer convenience layer (what a numpy caller binds).  A context owns one
  * CUDA stream plus pinned and device staging buffers that grow on demand. */
 typedef struct vcfb_ctx vcfb_ctx;
@@ -143,6 +157,11 @@ int vcfb_encode_host(vcfb_ctx* ctx, const uint8_t* rgb, int n_frames, int H, int
 int vcfb_decode_host(vcfb_ctx* ctx, const uint8_t* idx, int n_frames, int H, int W, int B,
                      double q, int color, unsigned flags, const double* weights,
                      uint8_t* rgb_out, void* y_out, const uint8_t* original, int64_t* stats);
+
+int vcfb_color_encode_host(vcfb_ctx* ctx, const uint8_t* rgb, long long n_pixels, double q, int color,
+                           uint16_t* k_out);
+int vcfb_color_decode_host(vcfb_ctx* ctx, const uint16_t* k, long long n_pixels, double q, int color,
+                           uint8_t* rgb_out);
 
 #ifdef __cplusplus
 }

@@ -295,3 +295,38 @@ def test_fast_decode_path(q, torch_cuda):
     got = _codec(block_size=8, q=300, fp64=True).decode(t.from_numpy(idx).cuda(), (16, 128))
     assert _lib.last_kernel() == "decode_general"
     assert np.array_equal(got.cpu().numpy(), O.decode_array(idx, img.shape, 8, 300))
+
+
+@pytest.mark.parametrize("color", ["YCoCg", "YCrCb"])
+def test_standalone_colour_codecs(color, torch_cuda, golden_dir):
+    """src/YCoCg.py:33-85 and src/YCrCb.py:33-69 as codecs of their own (SURVEY 8a rows A11,
+    A12): bit-exact against the vectors recorded from the unmodified reference scripts and
+    against the oracle on seeded inputs, incl. odd sizes and unaligned device pointers."""
+    from vcf_b200 import ColorCodec, _lib
+    t = torch_cuda
+    g = np.load(os.path.join(golden_dir, "ref_flow_sa_%s.npz" % color.lower()))
+    q = int([str(x) for x in g["flags"]][1])
+    cc = ColorCodec(color, q)
+    assert np.array_equal(cc.encode(g["img"]), g["idx"])
+    assert np.array_equal(cc.decode(g["idx"]), g["decoded"])
+    enc_o = O.ycocg_standalone_encode if color == "YCoCg" else O.ycrcb_standalone_encode
+    dec_o = O.ycocg_standalone_decode if color == "YCoCg" else O.ycrcb_standalone_decode
+    rng = np.random.default_rng(3)
+    for q in (1, 3, 8, 32, 200):
+        cc = ColorCodec(color, q)
+        for shape in ((1, 1, 3), (7, 5, 3), (64, 96, 3), (3, 217, 131, 3)):
+            img = rng.integers(0, 256, size=shape, dtype=np.uint8)
+            k = cc.encode(img)
+            assert k.dtype == np.uint16 and np.array_equal(k, enc_o(img.reshape(-1, 1, 3), q).reshape(shape))
+            assert _lib.last_kernel() == "color_encode"
+            assert np.array_equal(cc.decode(k), dec_o(k.reshape(-1, 1, 3), q).reshape(shape))
+            kr = rng.integers(0, 65536, size=shape, dtype=np.uint16)      # arbitrary indices: wrap paths
+            assert np.array_equal(cc.decode(kr), dec_o(kr.reshape(-1, 1, 3), q).reshape(shape))
+        # torch path, unaligned pointer
+        img = rng.integers(0, 256, size=(50, 70, 3), dtype=np.uint8)
+        buf = t.zeros(img.size + 16, dtype=t.uint8, device="cuda")
+        v = buf[1:1 + img.size].view(50, 70, 3)
+        v.copy_(t.from_numpy(img))
+        kt = cc.encode(v)
+        assert np.array_equal(kt.cpu().numpy(), enc_o(img, q))
+        assert np.array_equal(cc.decode(kt).cpu().numpy(), dec_o(enc_o(img, q), q))

@@ -55,6 +55,15 @@ def lib():
     L.vcfb_host_alloc.restype = i
     L.vcfb_host_free.argtypes = [vp]
     L.vcfb_host_free.restype = None
+    ll = C.c_longlong
+    L.vcfb_color_encode_dev.argtypes = [vp, ll, d, i, vp, vp]
+    L.vcfb_color_encode_dev.restype = i
+    L.vcfb_color_decode_dev.argtypes = [vp, ll, d, i, vp, vp]
+    L.vcfb_color_decode_dev.restype = i
+    L.vcfb_color_encode_host.argtypes = [vp, vp, ll, d, i, vp]
+    L.vcfb_color_encode_host.restype = i
+    L.vcfb_color_decode_host.argtypes = [vp, vp, ll, d, i, vp]
+    L.vcfb_color_decode_host.restype = i
     L.vcfb_encode_host.argtypes = [vp, vp, i, i, i, i, d, i, u, vp, vp, vp]
     L.vcfb_encode_host.restype = i
     L.vcfb_decode_host.argtypes = [vp, vp, i, i, i, i, d, i, u, vp, vp, vp, vp, vp]

@@ -266,6 +266,57 @@ class Codec:
         return res[0] if len(res) == 1 else tuple(res)
 
 
+class ColorCodec:
+    """Stand-alone colour codecs of the reference: ``python YCoCg.py encode|decode``
+    (src/YCoCg.py:33-85) and ``python YCrCb.py encode|decode`` (src/YCrCb.py:33-69):
+    colour transform + deadzone quantiser, uint8 RGB <-> uint16 indices, integer
+    arithmetic, bit-exact.  ``q`` must be integral (the reference's ``-q`` is)."""
+
+    def __init__(self, color: str = "YCoCg", q: int = 32, device: Optional[int] = None):
+        if color not in _COLORS:
+            raise ValueError(f"color must be one of {list(_COLORS)}")
+        if int(q) != q or not (0 < q < 32768):
+            raise ValueError("q must be an integer in [1, 32767]")
+        self.color, self.q, self.device, self._ctx = _COLORS[color], float(q), device, None
+
+    __del__ = Codec.__del__
+    _host_ctx = Codec._host_ctx
+
+    def _run(self, x, encode: bool):
+        L = _lib.lib()
+        if x.shape[-1] != 3:
+            raise ValueError("last dimension must be 3")
+        npx = int(np.prod(x.shape[:-1]))
+        if _is_torch(x):
+            import torch
+            want = torch.uint8 if encode else torch.uint16
+            if x.dtype != want or not x.is_cuda:
+                raise ValueError(f"torch input must be a CUDA {want} tensor")
+            x = x.contiguous()
+            out = torch.empty(x.shape, dtype=torch.uint16 if encode else torch.uint8, device=x.device)
+            with torch.cuda.device(x.device):
+                stream = torch.cuda.current_stream().cuda_stream
+                fn = L.vcfb_color_encode_dev if encode else L.vcfb_color_decode_dev
+                check(fn(x.data_ptr(), npx, self.q, self.color, out.data_ptr(), stream))
+            return out
+        want = np.uint8 if encode else np.uint16
+        if x.dtype != want:
+            raise ValueError(f"input must be {np.dtype(want)}")
+        x = np.ascontiguousarray(x)
+        out = np.empty(x.shape, dtype=np.uint16 if encode else np.uint8)
+        fn = L.vcfb_color_encode_host if encode else L.vcfb_color_decode_host
+        check(fn(self._host_ctx(), x.ctypes.data, npx, self.q, self.color, out.ctypes.data))
+        return out
+
+    def encode(self, rgb):
+        """uint8 RGB (...,3) -> uint16 indices (...,3)."""
+        return self._run(rgb, True)
+
+    def decode(self, k):
+        """uint16 indices (...,3) -> uint8 RGB (...,3)."""
+        return self._run(k, False)
+
+
 class _PinnedOwner:
     def __init__(self, ptr):
         self.ptr = ptr

@@ -129,6 +129,24 @@ int vcfb_decode_dev(const uint8_t* idx, int n_frames, int H, int W, int B, doubl
   return launch_decode_general(a, B, static_cast<cudaStream_t>(cuda_stream));
 }
 
+int vcfb_color_encode_dev(const uint8_t* rgb, long long n_pixels, double q, int color, uint16_t* k_out,
+                          void* cuda_stream) {
+  if (!rgb || !k_out) { set_error("NULL pointer"); return VCFB_E_ARG; }
+  if (n_pixels <= 0) { set_error("n_pixels must be > 0"); return VCFB_E_ARG; }
+  if (!(q > 0.0) || !isfinite(q)) { set_error("quantisation step q must be finite and > 0"); return VCFB_E_ARG; }
+  if (color != VCFB_COLOR_YCOCG && color != VCFB_COLOR_YCRCB) { set_error("unknown colour transform"); return VCFB_E_ARG; }
+  return launch_color_encode(rgb, n_pixels, q, color, k_out, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int vcfb_color_decode_dev(const uint16_t* k, long long n_pixels, double q, int color, uint8_t* rgb_out,
+                          void* cuda_stream) {
+  if (!k || !rgb_out) { set_error("NULL pointer"); return VCFB_E_ARG; }
+  if (n_pixels <= 0) { set_error("n_pixels must be > 0"); return VCFB_E_ARG; }
+  if (!(q > 0.0) || !isfinite(q)) { set_error("quantisation step q must be finite and > 0"); return VCFB_E_ARG; }
+  if (color != VCFB_COLOR_YCOCG && color != VCFB_COLOR_YCRCB) { set_error("unknown colour transform"); return VCFB_E_ARG; }
+  return launch_color_decode(k, n_pixels, q, color, rgb_out, static_cast<cudaStream_t>(cuda_stream));
+}
+
 // ---- host-buffer layer ----------------------------------------------------------
 //
 // A batch is cut into chunks of whole frames; chunk i runs on slot i % NSLOT
@@ -394,6 +412,52 @@ int vcfb_decode_host(vcfb_ctx* c, const uint8_t* idx, int n_frames, int H, int W
     }
   }
   return finish(c, d_st, stats);
+}
+
+int vcfb_color_encode_host(vcfb_ctx* c, const uint8_t* rgb, long long n_pixels, double q, int color,
+                           uint16_t* k_out) {
+  if (!c) { set_error("ctx is NULL"); return VCFB_E_ARG; }
+  if (!rgb || !k_out || n_pixels <= 0) { set_error("bad argument"); return VCFB_E_ARG; }
+  cudaError_t e = cudaSetDevice(c->device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  Slot* sl = &c->slot[0];
+  int rc = slot_drain(sl);
+  if (rc) return rc;
+  const size_t in_b = size_t(n_pixels) * 3, out_b = size_t(n_pixels) * 6, o_out = align256(in_b);
+  rc = slot_reserve(sl, o_out + out_b, 0);
+  if (rc) return rc;
+  e = cudaMemcpyAsync(sl->dev, rgb, in_b, cudaMemcpyHostToDevice, sl->s);
+  if (e != cudaSuccess) return cuda_fail(e, "host->device copy");
+  rc = vcfb_color_encode_dev(reinterpret_cast<uint8_t*>(sl->dev), n_pixels, q, color,
+                             reinterpret_cast<uint16_t*>(sl->dev + o_out), sl->s);
+  if (rc) return rc;
+  e = cudaMemcpyAsync(k_out, sl->dev + o_out, out_b, cudaMemcpyDeviceToHost, sl->s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(sl->s);
+  if (e != cudaSuccess) return cuda_fail(e, "colour encode (device->host / synchronize)");
+  return VCFB_OK;
+}
+
+int vcfb_color_decode_host(vcfb_ctx* c, const uint16_t* k, long long n_pixels, double q, int color,
+                           uint8_t* rgb_out) {
+  if (!c) { set_error("ctx is NULL"); return VCFB_E_ARG; }
+  if (!k || !rgb_out || n_pixels <= 0) { set_error("bad argument"); return VCFB_E_ARG; }
+  cudaError_t e = cudaSetDevice(c->device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  Slot* sl = &c->slot[0];
+  int rc = slot_drain(sl);
+  if (rc) return rc;
+  const size_t in_b = size_t(n_pixels) * 6, out_b = size_t(n_pixels) * 3, o_out = align256(in_b);
+  rc = slot_reserve(sl, o_out + out_b, 0);
+  if (rc) return rc;
+  e = cudaMemcpyAsync(sl->dev, k, in_b, cudaMemcpyHostToDevice, sl->s);
+  if (e != cudaSuccess) return cuda_fail(e, "host->device copy");
+  rc = vcfb_color_decode_dev(reinterpret_cast<uint16_t*>(sl->dev), n_pixels, q, color,
+                             reinterpret_cast<uint8_t*>(sl->dev + o_out), sl->s);
+  if (rc) return rc;
+  e = cudaMemcpyAsync(rgb_out, sl->dev + o_out, out_b, cudaMemcpyDeviceToHost, sl->s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(sl->s);
+  if (e != cudaSuccess) return cuda_fail(e, "colour decode (device->host / synchronize)");
+  return VCFB_OK;
 }
 
 }  // extern "C"

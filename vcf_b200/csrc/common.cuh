@@ -58,4 +58,8 @@ int launch_decode_general(const DecArgs& a, int B, cudaStream_t s);
 int launch_encode_fast(const EncArgs& a, int B, cudaStream_t s);
 int launch_decode_fast(const DecArgs& a, int B, cudaStream_t s);
 
+// stand-alone colour codecs (kernels_color.cu)
+int launch_color_encode(const uint8_t* rgb, long long npx, double q, int color, uint16_t* out, cudaStream_t s);
+int launch_color_decode(const uint16_t* k, long long npx, double q, int color, uint8_t* rgb, cudaStream_t s);
+
 }  // namespace vcfb
