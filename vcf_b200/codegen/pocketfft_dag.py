@@ -118,6 +118,9 @@ def const_value(sym, dtype):
     if kind == "fct":            # 1/sqrt(2N) in long double, rounded to T
         _, n = sym
         return dt(_LD(1) / np.sqrt(_LD(2 * n)))
+    if kind == "scaled":         # exact variant of another constant: sign * 2^k * value
+        _, inner, sign, k = sym
+        return dt(sign * 2.0 ** k) * const_value(inner, dtype)
     if kind == "sqrt2":
         return dt(_SQRT2_LD)
     if kind == "hsqt2":
@@ -446,7 +449,75 @@ def trace_dct(n: int, inverse: bool, in_exp: int = 0):
             a, b = c[k], c[k + 1]
             c[k] = g.sub(a, b)
             c[k + 1] = g.add(a, b)
-    return g, c
+    return make_unfusable(g, c)
+
+
+# ----------------------------------------------------------------------------
+# make multiply -> add chains unfusable
+# ----------------------------------------------------------------------------
+
+def _scaled(sym, sign, k):
+    if sym[0] == "scaled":
+        return _scaled(sym[1], sign * sym[2], k + sym[3])
+    return sym if (sign == 1 and k == 0) else ("scaled", sym, sign, k)
+
+
+def make_unfusable(g: Graph, outs):
+    """Rewrite the program so that no addition consumes the result of a constant multiply.
+
+    ptxas 12.9 fuses a packed ``mul.rn.f32x2`` into a following ``add.rn.f32x2`` (and into
+    ``fma.rn.f32x2`` with a factor of +1) despite the explicit rounding modifier, and
+    ``-fmad=false`` does not stop it; it does not touch ``fma(p, -1, a)``.  So every
+    ``a + c*x`` becomes ``a - (-c)*x`` (IEEE negation is exact and round-to-nearest is
+    sign-symmetric: same bits), and ``2^k*(c*x) + b`` becomes ``(2^k*c)*x + b`` first (the
+    power of two commutes with the rounding of the product).  Multiplies feeding more than
+    one consumer get a private negated copy.  The result is a new (graph, outputs)."""
+    live = live_nodes(g, outs)
+    ng = Graph()
+    m = {}
+
+    def mulneg(idx):
+        nd = g.nodes[idx]
+        return ng._mk(("mul", m[nd[1]], _scaled(nd[2], -1, 0)))
+
+    for idx, nd in enumerate(g.nodes):
+        if idx not in live:
+            continue
+        op = nd[0]
+        if op == "in":
+            m[idx] = ng._mk(nd)
+        elif op == "mul":
+            m[idx] = ng._mk(("mul", m[nd[1]], nd[2]))
+        elif op == "add":
+            a, b = nd[1], nd[2]
+            if g.nodes[b][0] == "mul":
+                m[idx] = ng._mk(("sub", m[a], mulneg(b)))
+            elif g.nodes[a][0] == "mul":
+                m[idx] = ng._mk(("sub", m[b], mulneg(a)))
+            else:
+                m[idx] = ng._mk(("add", m[a], m[b]))
+        elif op == "sub":
+            m[idx] = ng._mk(("sub", m[nd[1]], m[nd[2]]))
+        elif op == "fma2":
+            _, a, k, b, sa, sb = nd
+            if g.nodes[a][0] == "mul":          # (2^k * c) * x, exact
+                an = g.nodes[a]
+                if sb > 0:                       # sa*2^k*c*x + b  ->  b - (-sa*2^k*c)*x
+                    pa = ng._mk(("mul", m[an[1]], _scaled(an[2], -sa, k)))
+                    m[idx] = ng._mk(("sub", m[b], pa))
+                else:                            # 2^k*c*x - b      (sa is +1 here by construction)
+                    pa = ng._mk(("mul", m[an[1]], _scaled(an[2], sa, k)))
+                    m[idx] = ng._mk(("sub", pa, m[b]))
+            else:
+                m[idx] = ng._mk(("fma2", m[a], k, m[b], sa, sb))
+    nouts = [Val(m[o.node], o.sign, o.exp) for o in outs]
+    # post-condition: no add / fma2 has a multiply operand
+    for nd in ng.nodes:
+        if nd[0] == "add":
+            assert ng.nodes[nd[1]][0] != "mul" and ng.nodes[nd[2]][0] != "mul"
+        if nd[0] == "fma2":
+            assert ng.nodes[nd[1]][0] != "mul"
+    return ng, nouts
 
 
 # ----------------------------------------------------------------------------

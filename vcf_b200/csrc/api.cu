@@ -1,6 +1,7 @@
 // C ABI of libvcfb200 (include/vcfb200.h): argument checking, geometry, dispatch,
 // and the host-buffer convenience layer (pinned staging + one stream per context).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -158,7 +159,12 @@ int vcfb_color_decode_dev(const uint16_t* k, long long n_pixels, double q, int c
 
 namespace {
 constexpr int NSLOT = 3;
-constexpr size_t CHUNK_TARGET = size_t(96) << 20;   // bytes of input per chunk
+static size_t chunk_target() {
+  // bytes of input per chunk; VCFB_CHUNK_MB is a development knob
+  static size_t v = []() { const char* e = getenv("VCFB_CHUNK_MB"); return size_t(e ? atoi(e) : 32) << 20; }();
+  return v;
+}
+#define CHUNK_TARGET chunk_target()
 
 struct Slot {
   cudaStream_t s;
