@@ -330,3 +330,85 @@ def test_standalone_colour_codecs(color, torch_cuda, golden_dir):
         kt = cc.encode(v)
         assert np.array_equal(kt.cpu().numpy(), enc_o(img, q))
         assert np.array_equal(cc.decode(kt).cpu().numpy(), dec_o(enc_o(img, q), q))
+
+
+def test_config3_rde_sweep_full_size(torch_cuda):
+    """BASELINE config 3: 4K frame, B in {4,8,16,32} x 8 q values.  Exact index parity on
+    every point would take minutes of oracle time, so: exact parity for one q per B
+    (incl. a non-power-of-two), and for all 32 points the RD statistics of the GPU sweep
+    are checked against properties (RMSE monotone in q, rate estimate falling with q) and
+    against the oracle's RMSE on the points that were decoded."""
+    from vcf_b200.rd import rd_sweep
+    t = torch_cuda
+    H, W = 2160, 3840
+    img = O.synthetic_frame(H, W, 3, "natural")
+    x = t.from_numpy(img).cuda()
+    qs = (4, 8, 12, 16, 24, 32, 48, 64)
+    pts = rd_sweep(x, (4, 8, 16, 32), qs)
+    assert len(pts) == 32
+    for B in (4, 8, 16, 32):
+        row = [p for p in pts if p["B"] == B]
+        # over the power-of-two steps (nested dead zones) distortion grows and rate falls --
+        # for q >= B only: below that the DC index leaves [-128,127] and the reference's
+        # uint8 cast wraps (src/2D-DCT.py:361), e.g. RMSE 25.0 at B=8, q=4 vs 5.5 at q=8
+        p2 = [p for p in row if p["q"] in (4, 8, 16, 32, 64) and p["q"] >= B]
+        rm = [p["rmse"] for p in p2]
+        assert all(rm[i] < rm[i + 1] for i in range(len(rm) - 1)), (B, rm)
+        br = [p["bpp_entropy"] for p in p2]
+        assert all(br[i] > br[i + 1] for i in range(len(br) - 1)), (B, br)
+        assert all(0 < p["bpp_entropy"] < 24 and p["rmse"] > 0 for p in row)
+    for B, q in ((4, 12), (16, 24), (32, 48)):
+        ref = O.encode_array(img, B, q)
+        got = _codec(block_size=B, q=q).encode(x).cpu().numpy()
+        assert np.array_equal(got, ref), (B, q)
+        refd = O.decode_array(ref, img.shape, B, q)
+        dec = _codec(block_size=B, q=q, fp64=True).decode(t.from_numpy(ref).cuda(), (H, W)).cpu().numpy()
+        assert np.array_equal(dec, refd), (B, q)
+        p = [p for p in pts if p["B"] == B and p["q"] == q][0]
+        assert p["sse"] == O.sse_int(img, refd)
+        assert abs(p["rmse"] - float(O.rmse(img, refd))) < 1e-3
+
+
+def test_config5_8k_ycrcb_b16_full_size(torch_cuda):
+    """BASELINE config 5 shape: one 7680x4320 frame, YCrCb (float extension) + B=16, q=32:
+    exact parity with the oracle (float32 encode, float64 decode) and statistics."""
+    t = torch_cuda
+    H, W = 4320, 7680
+    img = O.synthetic_frame(H, W, 2000, "natural")
+    x = t.from_numpy(img).cuda()
+    enc = _codec(block_size=16, q=32, color="YCrCb")
+    got, st = enc.encode(x, stats=True)
+    ref = O.encode_array(img, 16, 32, color="YCrCb")
+    assert np.array_equal(got.cpu().numpy(), ref)
+    dec = _codec(block_size=16, q=32, color="YCrCb", fp64=True)
+    y, sd = dec.decode(got, (H, W), original=x, stats=True)
+    refd = O.decode_array(ref, img.shape, 16, 32, color="YCrCb")
+    assert np.array_equal(y.cpu().numpy(), refd)
+    from vcf_b200.codec import stats_dict
+    s = stats_dict((st + sd).cpu().numpy())
+    assert int(s["sse"].sum()) == O.sse_int(img, refd) and s["nsamples"] == img.size
+    nz, sabs, hist = O.index_stats(ref)
+    assert s["nonzero"] == nz and np.array_equal(s["hist"], hist)
+
+
+def test_config4_1080p_sequence_batch(torch_cuda):
+    """BASELINE config 4 shape: a batch of 1920x1080 frames (B=8, q=32; 1080 = 135*8).
+    Frame i of a batch must equal frame i coded alone (frames are independent,
+    src/III.py:132-144), and a few frames are checked exactly against the oracle."""
+    t = torch_cuda
+    n, H, W = 24, 1080, 1920
+    frames = np.stack([O.synthetic_frame(H, W, 1000 + i, "natural") for i in range(4)])
+    frames = np.concatenate([frames] * (n // 4))
+    frames[5] = O.synthetic_frame(H, W, 5, "noise")
+    x = t.from_numpy(frames).cuda()
+    enc, dec = _codec(block_size=8, q=32), _codec(block_size=8, q=32, fp64=True)
+    idx = enc.encode(x)
+    y = dec.decode(idx, (H, W))
+    for i in (0, 5, 23):
+        assert t.equal(idx[i], enc.encode(x[i]))
+        assert t.equal(y[i], dec.decode(idx[i], (H, W)))
+    for i in (1, 5):
+        ref = O.encode_array(frames[i], 8, 32)
+        assert np.array_equal(idx[i].cpu().numpy(), ref)
+        assert np.array_equal(y[i].cpu().numpy(), O.decode_array(ref, frames[i].shape, 8, 32))
+    assert t.equal(idx[0], idx[4]) and t.equal(y[1], y[9])          # identical frames, identical streams
