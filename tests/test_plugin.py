@@ -140,3 +140,26 @@ def test_plugin_against_the_real_reference_chain_cpu():
         _write_png("/tmp/original.png", img)
         r = _run(REF_SRC, PLUGIN, "encode", "-c", "z_lib", extra_path=(shims,))
         assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.gpu
+def test_batched_iii_driver_equals_per_frame_loop():
+    """vcf_b200/plugin/III-B200.py: the whole sequence as one GPU batch must write the same
+    files as the per-frame loop of src/III.py:132-144 (and the intended :96-104)."""
+    n = 5
+    frames = [O.synthetic_frame(72, 128, 80 + i, "natural" if i % 2 else "noise") for i in range(n)]
+    for i, f in enumerate(frames):
+        _write_png("/tmp/original_%04d.png" % i, f)
+        for ext in (".npz", "_shape.bin"):
+            if os.path.exists("/tmp/encoded_%04d%s" % (i, ext)):
+                os.remove("/tmp/encoded_%04d%s" % (i, ext))
+    iii = os.path.join(PLUGIN_DIR, "III-B200.py")
+    r = _run(STUB, iii, "encode", "-N", str(n), "-q", "16")
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = _run(STUB, iii, "decode", "-N", str(n), "-q", "16")
+    assert r.returncode == 0, r.stderr[-2000:]
+    for i, f in enumerate(frames):
+        assert struct.unpack("iii", open("/tmp/encoded_%04d_shape.bin" % i, "rb").read()) == f.shape
+        idx = np.load("/tmp/encoded_%04d.npz" % i)["a"]
+        assert np.array_equal(idx, O.encode_array(f, 8, 16))
+        assert np.array_equal(_read_png("/tmp/decoded_%04d.png" % i), O.decode_array(idx, f.shape, 8, 16))

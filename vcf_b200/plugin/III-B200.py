@@ -1,0 +1,134 @@
+'''III coding: runs a 2D image codec for each image of a sequence (all frames in one GPU batch).'''
+
+# Batched counterpart of the reference's src/III.py.  Same flags (-T transform, -N
+# number_of_frames, src/III.py:23-32), same file names (/tmp/original_%04d.png,
+# /tmp/encoded_%04d<ext> + _shape.bin, /tmp/decoded_%04d.png, :85-86, :133-134) and the same
+# per-frame results as calling the transform's encode_fn / decode_fn once per frame (what
+# :96-104 intends and :132-144 does) -- but the frames are read first, transformed as ONE
+# batch on the GPU (sharded by contiguous frame ranges over the ranks when launched with
+# torchrun, vcf_b200.frames), and entropy-coded / written by a pool of host threads.
+# The entropy coder and the file formats are the chain's own (compress / decompress /
+# encode_write_fn / decode_write_fn of the -c codec), so either side can be the reference.
+
+import importlib
+import logging
+import os
+import struct
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+_here = os.path.dirname(os.path.abspath(__file__))
+_repo = os.path.dirname(os.path.dirname(_here))
+for _p in (os.getcwd(), _here, _repo):
+    if _p not in sys.path:
+        sys.path.append(_p)
+
+import main  # noqa: E402
+with open("/tmp/description.txt", 'w') as f:
+    f.write(__doc__)
+import parser  # noqa: E402
+
+from vcf_b200.frames import frame_range  # noqa: E402
+
+DEFAULT_TRANSFORM = "2D-DCT-B200"
+N_FRAMES = 20                      # src/video_coding.py:29
+ORIGINAL_PREFIX = "/tmp/original"  # frames extracted by src/III.py:85
+ENCODE_OUTPUT_PREFIX = "/tmp/encoded"
+DECODE_OUTPUT_PREFIX = "/tmp/decoded"
+
+for _p in (parser.parser_encode, parser.parser_decode):
+    _p.add_argument("-T", "--transform", type=str, help=f"2D-transform, default: {DEFAULT_TRANSFORM}", default=DEFAULT_TRANSFORM)
+    _p.add_argument("-N", "--number_of_frames", type=parser.int_or_str, help=f"Number of frames (default: {N_FRAMES})", default=N_FRAMES)
+    _p.add_argument("--io_threads", type=int, default=8, help="host threads for entropy coding and file IO")
+
+args = parser.parser.parse_known_args()[0]
+transform = importlib.import_module(args.transform)
+
+
+def _rank_world():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+class CoDec:
+
+    def __init__(self, args):
+        logging.debug("trace")
+        self.args = args
+        self.transform_codec = transform.CoDec(args)
+        if not hasattr(self.transform_codec, "_codec"):
+            raise TypeError("III-B200 batches through the GPU transform; use -T 2D-DCT-B200")
+        logging.info(f"Using {args.transform} codec")
+
+    def bye(self):
+        pass
+
+    def _extract_frames(self, n):
+        """src/III.py:73-115: demux args.original with PyAV into /tmp/original_%04d.png --
+        only when the frames are not there yet and PyAV is installed."""
+        if all(os.path.exists(f"{ORIGINAL_PREFIX}_%04d.png" % i) for i in range(n)):
+            return
+        import av  # not a dependency of the GPU path
+        import cv2
+        container = av.open(self.args.original)
+        i = 0
+        for frame in container.decode(video=0):
+            img = np.array(frame.to_image().convert("RGB"))
+            cv2.imwrite(f"{ORIGINAL_PREFIX}_%04d.png" % i, cv2.cvtColor(img, cv2.COLOR_RGB2BGR))
+            i += 1
+            if i >= n:
+                break
+
+    def encode(self):
+        tc = self.transform_codec
+        n = int(self.args.number_of_frames)
+        rank, world = _rank_world()
+        if rank == 0:
+            self._extract_frames(n)
+        lo, hi = frame_range(n, rank, world)
+        if hi == lo:
+            return 0
+        with ThreadPoolExecutor(self.args.io_threads) as pool:
+            frames = list(pool.map(lambda i: tc.encode_read_fn(f"{ORIGINAL_PREFIX}_%04d.png" % i), range(lo, hi)))
+            for fr in frames:
+                tc._check_image(fr)
+            if len({fr.shape for fr in frames}) != 1:
+                raise ValueError("all frames of a sequence must have the same shape")
+            idx = tc._codec().encode(np.ascontiguousarray(np.stack(frames)))    # one GPU batch
+
+            def finish(j):
+                out_fn = f"{ENCODE_OUTPUT_PREFIX}_%04d" % (lo + j)
+                with open(f"{out_fn}_shape.bin", "wb") as file:
+                    file.write(struct.pack("iii", *frames[j].shape))
+                return tc.encode_write_fn(tc.compress(idx[j]), out_fn)
+            sizes = list(pool.map(finish, range(hi - lo)))
+        logging.info(f"rank {rank}: frames [{lo},{hi}) -> {sum(sizes)} bytes")
+        return sum(sizes)
+
+    def decode(self):
+        tc = self.transform_codec
+        n = int(self.args.number_of_frames)
+        rank, world = _rank_world()
+        lo, hi = frame_range(n, rank, world)
+        if hi == lo:
+            return 0
+        with ThreadPoolExecutor(self.args.io_threads) as pool:
+            def load(i):
+                in_fn = f"{ENCODE_OUTPUT_PREFIX}_%04d" % i
+                with open(f"{in_fn}_shape.bin", "rb") as file:
+                    shape = struct.unpack("iii", file.read(12))
+                return shape, np.ascontiguousarray(tc.decompress(tc.decode_read_fn(in_fn)))
+            items = list(pool.map(load, range(lo, hi)))
+            shapes = {s for s, _ in items}
+            if len(shapes) != 1:
+                raise ValueError("all frames of a sequence must have the same shape")
+            shape = shapes.pop()
+            y = tc._codec(decode=True).decode(np.stack([k for _, k in items]), shape[:2])   # one GPU batch
+            sizes = list(pool.map(lambda j: tc.decode_write_fn(y[j], f"{DECODE_OUTPUT_PREFIX}_%04d.png" % (lo + j)),
+                                  range(hi - lo)))
+        return sum(sizes)
+
+
+if __name__ == "__main__":
+    main.main(parser.parser, logging, CoDec)
