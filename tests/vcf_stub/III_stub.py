@@ -10,7 +10,7 @@ for p in (parser.parser_encode, parser.parser_decode):
     p.add_argument("-T", "--transform", type=str, default="2D-DCT-B200")
     p.add_argument("-N", "--number_of_frames", type=parser.int_or_str, default=3)
 args = parser.parser.parse_known_args()[0]
-transform = importlib.import_module(args.transform)
+transform = importlib.import_module(args.transform)  # registers -t etc.
 
 
 class CoDec:

@@ -1,4 +1,4 @@
-'''Exploiting spatial redundancy with the 2D Discrete Cosine Transform of constant block size (B200-native arithmetic).'''
+'''Block-DCT spatial stage (fixed block size) with the colour / DCT / deadzone arithmetic on a B200 GPU.'''
 
 # Drop-in replacement of the reference's src/2D-DCT.py: same flags and dests
 # (src/2D-DCT.py:36-45), same class chain (``class CoDec(CT.CoDec)``, CT chosen by
@@ -44,11 +44,11 @@ disable_subbands = False
 SUPPORTED_B = (4, 8, 16, 32)
 
 for _p in (parser.parser_encode, parser.parser_decode):
-    _p.add_argument("-B", "--block_size_DCT", type=parser.int_or_str, help=f"Block size (default: {default_block_size})", default=default_block_size)
-    _p.add_argument("-t", "--color_transform", type=parser.int_or_str, help=f"Color transform (default: \"{default_CT}\")", default=default_CT)
-    _p.add_argument("-p", "--perceptual_quantization", action='store_true', help=f"Use perceptual (de)quantization (default: \"{perceptual_quantization}\")", default=perceptual_quantization)
-    _p.add_argument("-x", "--disable_subbands", action='store_true', help=f"Disable the coefficients reordering in subbands (default: \"{disable_subbands}\")", default=disable_subbands)
-parser.parser_encode.add_argument("-L", "--Lambda", type=parser.int_or_str, help="Relative weight between the rate and the distortion. If provided (float), the block size is RD-optimized between the block sizes the GPU path supports (4, 8, 16, 32).")
+    _p.add_argument("-B", "--block_size_DCT", type=parser.int_or_str, help=f"side of the square DCT blocks: 4, 8, 16 or 32 (default {default_block_size})", default=default_block_size)
+    _p.add_argument("-t", "--color_transform", type=parser.int_or_str, help=f"module providing the colour stage / base class (default {default_CT})", default=default_CT)
+    _p.add_argument("-p", "--perceptual_quantization", action='store_true', help="weight the coefficients with the JPEG luma / chroma tables before quantising", default=perceptual_quantization)
+    _p.add_argument("-x", "--disable_subbands", action='store_true', help="keep the coefficients in block order instead of grouping them by subband", default=disable_subbands)
+parser.parser_encode.add_argument("-L", "--Lambda", type=parser.int_or_str, help="when given (float): pick the block size in {4, 8, 16, 32} minimising bytes + Lambda * RMSE")
 parser.parser_decode.add_argument("--b200_fast_decode", action='store_true', help="float32 GPU decoder (pixels within +-1 of the reference) instead of the bit-exact float64 one", default=False)
 
 args = parser.parser.parse_known_args()[0]

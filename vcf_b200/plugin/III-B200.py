@@ -1,4 +1,4 @@
-'''III coding: runs a 2D image codec for each image of a sequence (all frames in one GPU batch).'''
+'''Intra-only sequence coding: every frame goes through the 2D codec, the whole sequence as one GPU batch.'''
 
 # Batched counterpart of the reference's src/III.py.  Same flags (-T transform, -N
 # number_of_frames, src/III.py:23-32), same file names (/tmp/original_%04d.png,
@@ -39,8 +39,8 @@ ENCODE_OUTPUT_PREFIX = "/tmp/encoded"
 DECODE_OUTPUT_PREFIX = "/tmp/decoded"
 
 for _p in (parser.parser_encode, parser.parser_decode):
-    _p.add_argument("-T", "--transform", type=str, help=f"2D-transform, default: {DEFAULT_TRANSFORM}", default=DEFAULT_TRANSFORM)
-    _p.add_argument("-N", "--number_of_frames", type=parser.int_or_str, help=f"Number of frames (default: {N_FRAMES})", default=N_FRAMES)
+    _p.add_argument("-T", "--transform", type=str, help=f"module of the 2D codec (default {DEFAULT_TRANSFORM})", default=DEFAULT_TRANSFORM)
+    _p.add_argument("-N", "--number_of_frames", type=parser.int_or_str, help=f"how many frames of the sequence to code (default {N_FRAMES})", default=N_FRAMES)
     _p.add_argument("--io_threads", type=int, default=8, help="host threads for entropy coding and file IO")
 
 args = parser.parser.parse_known_args()[0]
