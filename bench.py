@@ -35,6 +35,18 @@ sys.path.insert(0, ROOT)
 
 H, W, B = 2160, 3840, 8
 QS = (8, 16, 32, 64)
+COLOR = "YCoCg"
+# workload -> (H, W, B, qs, colour, statistics + all-reduce, default frames per GPU per step, description)
+WORKLOADS = {
+    "c2": (2160, 3840, 8, (8, 16, 32, 64), "YCoCg", False, 64,
+           "configs[1]: 3840x2160 RGB, YCoCg, B=8, q in {8,16,32,64} cycled per step, encode+decode"),
+    "rde": (2160, 3840, 8, (8, 16, 32, 64), "YCoCg", True, 64,
+            "configs[1] frames + RD statistics (SSE, index histogram) + NCCL all-reduce per batch"),
+    "c4": (1080, 1920, 8, (32,), "YCoCg", False, 128,
+           "configs[3]: 1920x1080 intra frames, YCoCg, B=8, q=32, frame-parallel"),
+    "c5": (4320, 7680, 16, (32,), "YCrCb", True, 8,
+           "configs[4]: 7680x4320 frames, YCrCb (float extension) + B=16, q=32, RD statistics all-reduced"),
+}
 ALG_BYTES_PER_PX = {"encode": 6.0, "decode": 6.0}    # 3 B read + 3 B written each
 
 
@@ -44,12 +56,12 @@ def parse():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames", type=int, default=64, help="4K frames per GPU per step")
+    ap.add_argument("--frames", type=int, default=0, help="frames per GPU per step (0 = workload default)")
     ap.add_argument("--e2e-frames", type=int, default=16, help="4K frames per GPU per end-to-end step")
     ap.add_argument("--decode", default="fp64", choices=["fp32", "fp64"],
                     help="decoder arithmetic: fp32 (+-1 LSB) or fp64 (the reference's chain, bit-exact)")
     ap.add_argument("--contract", action="store_true", help="encoder: allow fused multiply-adds (VCFB_F_CONTRACT)")
-    ap.add_argument("--workload", default="c2", choices=["c2", "rde"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=20.0)
     return ap.parse_args()
@@ -194,7 +206,7 @@ def run_reference(a):
     per_step = []
     base = None
     for s in range(a.warmup + a.steps):
-        base = cpu_oracle_throughput(a.cpu_seconds / max(1, a.steps), q=QS[s % 4])
+        base = cpu_oracle_throughput(a.cpu_seconds / max(1, a.steps), q=QS[s % len(QS)])
         if s >= a.warmup:
             per_step.append(base["value"])
     v = sum(per_step) / len(per_step)
@@ -255,18 +267,22 @@ def run_ours(a):
 
     n = a.frames
     fp64_dec = a.decode == "fp64"
-    enc = {q: Codec(block_size=B, q=q, contract=a.contract) for q in QS}
-    dec = {q: Codec(block_size=B, q=q, fp64=fp64_dec) for q in QS}
+    # statistics of the rde / c5 workloads: SSE + non-zero count + sum |k| (the quantities
+    # src/IPP_DCT.py:273-292 estimates bits from); the per-sample histogram stays off
+    enc = {q: Codec(block_size=B, q=q, contract=a.contract, color=COLOR, hist=False) for q in QS}
+    dec = {q: Codec(block_size=B, q=q, fp64=fp64_dec, color=COLOR) for q in QS}
     x = make_frames(torch, n, dev, 1234 + rank)
-    idx = torch.empty((n, H, W, 3), dtype=torch.uint8, device=dev)
+    Hp, Wp = (H + B - 1) // B * B, (W + B - 1) // B * B
+    idx = torch.empty((n, Hp, Wp, 3), dtype=torch.uint8, device=dev)
     y = torch.empty((n, H, W, 3), dtype=torch.uint8, device=dev)
-    rde = a.workload == "rde"
+    rde = a.rde
+    NQ = len(QS)
     launches = 0
     kernels_seen = {}
 
     def step(s, ev=None):
         nonlocal launches
-        q = QS[s % 4]
+        q = QS[s % NQ]
         if ev:
             ev[0].record()
         kn = kernels_seen
@@ -331,14 +347,14 @@ def run_ours(a):
     ne = a.e2e_frames
     hx = torch.empty((ne, H, W, 3), dtype=torch.uint8, pin_memory=True)
     hx.copy_(x[:ne])
-    hidx = torch.empty((ne, H, W, 3), dtype=torch.uint8, pin_memory=True)
+    hidx = torch.empty((ne, Hp, Wp, 3), dtype=torch.uint8, pin_memory=True)
     hy = torch.empty((ne, H, W, 3), dtype=torch.uint8, pin_memory=True)
     hxn, hidxn, hyn = hx.numpy(), hidx.numpy(), hy.numpy()
-    enc_h = {q: Codec(block_size=B, q=q, contract=a.contract, device=local) for q in QS}
-    dec_h = {q: Codec(block_size=B, q=q, fp64=fp64_dec, device=local) for q in QS}
+    enc_h = {q: Codec(block_size=B, q=q, contract=a.contract, device=local, color=COLOR) for q in QS}
+    dec_h = {q: Codec(block_size=B, q=q, fp64=fp64_dec, device=local, color=COLOR) for q in QS}
 
     def e2e_step(s):
-        q = QS[s % 4]
+        q = QS[s % NQ]
         enc_h[q].encode(hxn, out=hidxn)
         dec_h[q].decode(hidxn, (H, W), out=hyn)
 
@@ -355,7 +371,7 @@ def run_ours(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     e2e_val = world * ne * H * W * a.steps / 1e6 / e2e_s
-    same = bool(torch.equal(hy[:1].to(dev), y[:1])) if a.steps % 4 == 0 else None
+    same = bool(torch.equal(hy[:1].to(dev), y[:1])) if a.steps % NQ == 0 else None
 
     if rank != 0:
         if world > 1:
@@ -393,8 +409,7 @@ def run_ours(a):
             "dtype": f"f32 encode ({'contracted' if a.contract else 'bit-exact with the reference float32 path'}) / "
                      f"{'f64 (reference chain, bit-exact)' if fp64_dec else 'f32 (+-1 LSB)'} decode",
             "data": "synthetic",
-            "config": {"workload": ("configs[1]: 3840x2160 RGB, YCoCg, B=8, q in {8,16,32,64} cycled per step, "
-                                    "encode+decode" + (", RD statistics + NCCL all-reduce" if rde else "")),
+            "config": {"workload": a.workload_desc,
                        "frames_per_gpu_per_step": n, "parallelism": f"frame-parallel x{world}",
                        "l2": f"inputs exceed L2: {3 * n * H * W * 3 / 1e9:.1f} GB touched per step vs 126 MB"},
             "clocks": clocks,
@@ -412,7 +427,12 @@ def run_ours(a):
 
 
 def main():
+    global H, W, B, QS, COLOR
     a = parse()
+    H, W, B, QS, COLOR, a.rde, dflt, a.workload_desc = WORKLOADS[a.workload]
+    if a.frames <= 0:
+        a.frames = dflt
+    a.e2e_frames = max(1, min(a.e2e_frames, a.frames))
     if a.gpus > 1 and "WORLD_SIZE" not in os.environ:
         import socket
         s = socket.socket()

@@ -61,6 +61,9 @@ extern "C" {
                                  with the reference's float32 path (:276); with it
                                  < 1e-6 of the indices may differ. */
 
+#define VCFB_F_HIST 16u       /* statistics: also accumulate the 3 x 256 histogram of the indices
+                                 (one shared-memory atomic per sample; off = only the sums) */
+
 /* statistics vector (int64), accumulated with integer atomics; the caller zeroes it.
  * Integer sums make the multi-GPU all-reduce order-independent. */
 #define VCFB_STAT_SSE_R 0      /* sum (original - decoded)^2, channel R  (src/RDE.py:41-49) */
@@ -100,8 +103,8 @@ int vcfb_padded_dims(int H, int W, int B, int* Hp, int* Wp, int* top, int* left)
  * weights  2*B*B doubles, device: Y_QSSs/121 then C_QSSs/99 (src/2D-DCT.py:322-324),
  *          row-major [j][i]; NULL unless VCFB_F_PERCEPTUAL
  * idx_out  (n_frames,Hp,Wp,3) uint8, device
- * stats    VCFB_STAT_LEN int64 on the device or NULL; adds NONZERO, SUMABS,
- *          NINDICES and HIST */
+ * stats    VCFB_STAT_LEN int64 on the device or NULL; adds NONZERO, SUMABS, NINDICES
+ *          and, with VCFB_F_HIST, HIST */
 int vcfb_encode_dev(const uint8_t* rgb, int n_frames, int H, int W, int B, double q,
                     int color, unsigned flags, const double* weights,
                     uint8_t* idx_out, int64_t* stats, void* cuda_stream);

@@ -412,3 +412,35 @@ def test_config4_1080p_sequence_batch(torch_cuda):
         assert np.array_equal(idx[i].cpu().numpy(), ref)
         assert np.array_equal(y[i].cpu().numpy(), O.decode_array(ref, frames[i].shape, 8, 32))
     assert t.equal(idx[0], idx[4]) and t.equal(y[1], y[9])          # identical frames, identical streams
+
+
+def test_fast_path_statistics(torch_cuda):
+    """Statistics requested on a fast-path shape: the TMA kernels run, followed by the
+    streaming statistics kernels; every number must equal the oracle's (and the general
+    kernels' for the same input)."""
+    from vcf_b200 import _lib
+    from vcf_b200.codec import stats_dict
+    t = torch_cuda
+    for (n, H, W, q) in ((3, 64, 256, 16), (1, 1080, 1920, 8)):
+        frames = np.stack([O.synthetic_frame(H, W, 1200 + i, "natural" if i % 2 == 0 else "noise") for i in range(n)])
+        x = t.from_numpy(frames).cuda()
+        ref = np.stack([O.encode_array(f, 8, q) for f in frames])
+        refd = np.stack([O.decode_array(k, (H, W, 3), 8, q) for k in ref])
+        nz, sabs, hist = O.index_stats(ref)
+        for use_hist in (True, False):
+            enc = _codec(block_size=8, q=q, hist=use_hist)
+            idx, st = enc.encode(x, stats=True)
+            assert _lib.last_kernel() == "enc8_fast"
+            assert np.array_equal(idx.cpu().numpy(), ref)
+            s = stats_dict(st.cpu().numpy())
+            assert s["nonzero"] == nz and s["sumabs"] == sabs and s["nindices"] == ref.size
+            assert np.array_equal(s["hist"], hist if use_hist else np.zeros_like(hist))
+        dec = _codec(block_size=8, q=q, fp64=True)
+        y, sd = dec.decode(idx, (H, W), original=x, stats=True)
+        assert _lib.last_kernel() == "dec8_fast"
+        assert np.array_equal(y.cpu().numpy(), refd)
+        s = stats_dict(sd.cpu().numpy())
+        for c in range(3):
+            assert int(s["sse"][c]) == O.sse_int(frames[..., c], refd[..., c])
+        assert s["nsamples"] == frames.size
+        assert s["sumdiff"] == int((frames.astype(np.int64) - refd.astype(np.int64)).sum())

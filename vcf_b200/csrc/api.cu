@@ -45,7 +45,7 @@ static int check_common(const void* in, int n_frames, int H, int W, int B, doubl
   if (color != VCFB_COLOR_YCOCG && color != VCFB_COLOR_YCRCB) { set_error("unknown colour transform"); return VCFB_E_ARG; }
   if ((flags & VCFB_F_PERCEPTUAL) && !weights) { set_error("VCFB_F_PERCEPTUAL needs weights"); return VCFB_E_ARG; }
   if ((flags & VCFB_F_FP64) && (flags & VCFB_F_CONTRACT)) { set_error("VCFB_F_CONTRACT is float32 only"); return VCFB_E_ARG; }
-  if (flags & ~(VCFB_F_NO_SUBBANDS | VCFB_F_PERCEPTUAL | VCFB_F_FP64 | VCFB_F_CONTRACT)) { set_error("unknown flag bits"); return VCFB_E_ARG; }
+  if (flags & ~(VCFB_F_NO_SUBBANDS | VCFB_F_PERCEPTUAL | VCFB_F_FP64 | VCFB_F_CONTRACT | VCFB_F_HIST)) { set_error("unknown flag bits"); return VCFB_E_ARG; }
   return VCFB_OK;
 }
 

@@ -667,9 +667,15 @@ static int launch_enc_t(bool exact, bool qpow2, const CUtensorMap& in_map, const
 int launch_encode_fast(const EncArgs& a, int B, cudaStream_t s) {
   if (B != 8 || a.color != VCFB_COLOR_YCOCG) return VCFB_E_UNSUPP;
   if (a.flags & (VCFB_F_NO_SUBBANDS | VCFB_F_PERCEPTUAL | VCFB_F_FP64)) return VCFB_E_UNSUPP;
-  if (a.stats) return VCFB_E_UNSUPP;
   const Geom& g = a.g;
   if (!fast_geometry_ok(g, a.rgb, a.idx)) return VCFB_E_UNSUPP;
+  if (a.stats) {   // statistics are a separate streaming pass over the indices (kernels_stats.cu)
+    EncArgs b = a;
+    b.stats = nullptr;
+    int rc = launch_encode_fast(b, B, s);
+    if (rc) return rc;
+    return launch_index_stats(a.idx, (long long)a.n_frames * g.Hp * g.Wp * 3, (a.flags & VCFB_F_HIST) != 0, a.stats, s);
+  }
   CUtensorMap in_map, out_map;
   if (!make_rgb_map(&in_map, g, a.n_frames, a.rgb)) return VCFB_E_UNSUPP;
   if (!make_idx_map(&out_map, g, a.n_frames, a.idx, true)) return VCFB_E_UNSUPP;
@@ -742,9 +748,19 @@ static int launch_dec_f64h(const CUtensorMap& in_map, const CUtensorMap& out_map
 int launch_decode_fast(const DecArgs& a, int B, cudaStream_t s) {
   if (B != 8 || a.color != VCFB_COLOR_YCOCG) return VCFB_E_UNSUPP;
   if (a.flags & (VCFB_F_NO_SUBBANDS | VCFB_F_PERCEPTUAL)) return VCFB_E_UNSUPP;
-  if (a.stats || a.original || a.y_out || !a.rgb) return VCFB_E_UNSUPP;
+  if (a.y_out || !a.rgb) return VCFB_E_UNSUPP;
+  if ((a.stats != nullptr) != (a.original != nullptr)) return VCFB_E_UNSUPP;
   if (a.q_int < 1 || a.q_int > 255) return VCFB_E_UNSUPP;
   const Geom& g = a.g;
+  if (a.stats) {   // distortion = a separate streaming pass over (original, decoded)
+    if (reinterpret_cast<uintptr_t>(a.original) & 15) return VCFB_E_UNSUPP;
+    DecArgs b = a;
+    b.stats = nullptr;
+    b.original = nullptr;
+    int rc = launch_decode_fast(b, B, s);
+    if (rc) return rc;
+    return launch_sse(a.original, a.rgb, (long long)a.n_frames * g.H * g.W * 3, a.stats, s);
+  }
   // (a TMA store whose box starts at a negative row faults on sm_100a, so frames with
   //  vertical padding take the general kernel)
   if (!fast_geometry_ok(g, a.rgb, a.idx) || g.top != 0) return VCFB_E_UNSUPP;

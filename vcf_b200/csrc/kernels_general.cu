@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(NT) encode_kernel(const EncArgs a) {
   const bool nosub = (a.flags & VCFB_F_NO_SUBBANDS) != 0;
   const bool percep = (a.flags & VCFB_F_PERCEPTUAL) != 0;
   const bool do_stats = a.stats != nullptr;
+  const bool do_hist = do_stats && (a.flags & VCFB_F_HIST) != 0;
   const int nruns = nosub ? B : B * B;
   const int runlen = nosub ? nbx * B * 3 : nbx * 3;
   const int rpitch = nosub ? L::RP_NOSUB : L::RP_SUB;
@@ -240,7 +241,7 @@ __global__ void __launch_bounds__(NT) encode_kernel(const EncArgs a) {
             const int kk = int(byte) - 128;
             nz += (kk != 0);
             sabs += unsigned(kk < 0 ? -kk : kk);
-            atomicAdd(&shist[c * 256 + byte], 1u);
+            if (do_hist) atomicAdd(&shist[c * 256 + byte], 1u);
           }
         }
       }
@@ -275,8 +276,9 @@ __global__ void __launch_bounds__(NT) encode_kernel(const EncArgs a) {
       atomicAdd(&sacc[1], sabs);
     }
     __syncthreads();
-    for (int i = tid; i < 3 * 256; i += NT)
-      if (shist[i]) atomicAdd(a.stats + VCFB_STAT_HIST + i, (unsigned long long)shist[i]);
+    if (do_hist)
+      for (int i = tid; i < 3 * 256; i += NT)
+        if (shist[i]) atomicAdd(a.stats + VCFB_STAT_HIST + i, (unsigned long long)shist[i]);
     if (tid == 0) {
       atomicAdd(a.stats + VCFB_STAT_NONZERO, (unsigned long long)sacc[0]);
       atomicAdd(a.stats + VCFB_STAT_SUMABS, (unsigned long long)sacc[1]);
