@@ -28,7 +28,7 @@ namespace {
 
 constexpr int NT = 256;
 
-__host__ __device__ constexpr int tile_w(int B, int szT) { return (B == 32 && szT == 8) ? 128 : 256; }
+__host__ __device__ constexpr int tile_w(int B, int szT) { return (B >= 16 && szT == 8) ? 128 : 256; }
 
 __host__ __device__ constexpr double p2(int e) {
   double r = 1.0;
@@ -37,6 +37,8 @@ __host__ __device__ constexpr double p2(int e) {
 }
 
 __host__ __device__ constexpr int round16(int x) { return (x + 15) / 16 * 16; }
+// smallest odd multiple of 16 bytes >= x: rows of such a pitch start in different banks
+__host__ __device__ constexpr int round16_odd(int x) { return ((round16(x) / 16) | 1) * 16; }
 
 template <typename T, int B> struct Layout {
   static constexpr int TW = tile_w(B, sizeof(T));
@@ -44,10 +46,22 @@ template <typename T, int B> struct Layout {
   static constexpr int RAWP = TW * 3;                    // encode input row pitch (bytes)
   static constexpr int OUTP = TW * 3 + 16;               // decode output row pitch (bytes)
   static constexpr int FP = TW + 16 / int(sizeof(T));    // pitch of the intermediate (elements)
-  static constexpr int RP_SUB = round16(TBX * 3 + 15);   // run pitch, subband layout
+  static constexpr int RP_SUB = round16_odd(TBX * 3 + 15);   // run pitch, subband layout
   static constexpr int RP_NOSUB = round16(TW * 3 + 15);  // run pitch, -x layout
   static constexpr int STAGE = (B * B * RP_SUB > B * RP_NOSUB) ? B * B * RP_SUB : B * RP_NOSUB;
   static constexpr int F_BYTES = 3 * B * FP * int(sizeof(T));
+  // 16-byte chunks per block row of the intermediate, and the XOR key that spreads the
+  // chunks of 8 consecutive blocks over the 8 bank groups (pass 2 of the encoder reads one
+  // block row per lane, lanes = consecutive blocks)
+  static constexpr int VEC = 16 / int(sizeof(T));
+  static constexpr int CPB = B / VEC;
+  __host__ __device__ static constexpr int key(int bx) {
+    return CPB <= 1 ? 0 : (CPB <= 8 ? ((bx * CPB / 8) & (CPB - 1)) : (bx & 7));
+  }
+  // physical column of logical column x (x = bx * B + i)
+  __host__ __device__ static constexpr int swz(int x) {
+    return (x / B) * B + ((((x % B) / VEC) ^ key(x / B)) * VEC) + (x % VEC);
+  }
   static constexpr int SHIFT_BYTES = B * B * 4;
   static constexpr int ENC_SMEM = B * RAWP + F_BYTES + STAGE + SHIFT_BYTES + 4 * 256 * 3 + 64;
   static constexpr int DEC_SMEM = B * OUTP + F_BYTES + STAGE + SHIFT_BYTES + B * 4 + 64;
@@ -171,22 +185,43 @@ __global__ void __launch_bounds__(NT) encode_kernel(const EncArgs a) {
   __syncthreads();
 
   // ---- pass 1: colour + DCT down each pixel column (axis 0) -----------------
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const T cs = T(a.color == VCFB_COLOR_YCOCG ? (c == 1 ? 0.5 : 0.25) : 1.0);
+  constexpr bool JOINT = 3 * B * int(sizeof(T)) <= 4 * 96;     // all three channels in registers
+  if (JOINT) {
     for (int x = tid; x < TW; x += NT) {
-      T v[B];
+      T v[3][B];
 #pragma unroll
       for (int r = 0; r < B; ++r) {
         const uint8_t* px = raw + r * RAWP + x * 3;
-        v[r] = color_fwd<T, EXACT>(a.color, c, px[0], px[1], px[2]);
-      }
-      D::template run<T, EXACT>(v);
+        const int R = px[0], G = px[1], Bc = px[2];
 #pragma unroll
-      for (int u = 0; u < B; ++u) {
-        // exact: power-of-two factor (lazy codelet scale x lazy colour scale)
-        const T s = T(M::sgn(u) * p2(M::exp(u))) * cs;
-        F[(c * B + u) * FP + x] = O::mul(v[u], s);
+        for (int c = 0; c < 3; ++c) v[c][r] = color_fwd<T, EXACT>(a.color, c, R, G, Bc);
+      }
+      const int xs = L::swz(x);
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const T cs = T(a.color == VCFB_COLOR_YCOCG ? (c == 1 ? 0.5 : 0.25) : 1.0);
+        D::template run<T, EXACT>(v[c]);
+#pragma unroll
+        for (int u = 0; u < B; ++u)
+          F[(c * B + u) * FP + xs] = O::mul(v[c][u], T(M::sgn(u) * p2(M::exp(u))) * cs);   // exact factor
+      }
+    }
+  } else {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const T cs = T(a.color == VCFB_COLOR_YCOCG ? (c == 1 ? 0.5 : 0.25) : 1.0);
+      for (int x = tid; x < TW; x += NT) {
+        T v[B];
+#pragma unroll
+        for (int r = 0; r < B; ++r) {
+          const uint8_t* px = raw + r * RAWP + x * 3;
+          v[r] = color_fwd<T, EXACT>(a.color, c, px[0], px[1], px[2]);
+        }
+        D::template run<T, EXACT>(v);
+        const int xs = L::swz(x);
+#pragma unroll
+        for (int u = 0; u < B; ++u)
+          F[(c * B + u) * FP + xs] = O::mul(v[u], T(M::sgn(u) * p2(M::exp(u))) * cs);       // exact factor
       }
     }
   }
@@ -201,14 +236,15 @@ __global__ void __launch_bounds__(NT) encode_kernel(const EncArgs a) {
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
       for (int t = tid; t < TW; t += NT) {
-        const int u = t % B, bx = t / B;
+        const int bx = t % TBX, u = t / TBX;      // lanes = consecutive blocks: conflict-free staging stores
         if (bx >= nbx) continue;
         T v[B];
         const T* src = F + (c * B + u) * FP + bx * B;
-        constexpr int VEC = 16 / int(sizeof(T));
+        constexpr int VEC = L::VEC;
+        const int key = L::key(bx);
 #pragma unroll
         for (int i = 0; i < B; i += VEC) {
-          const uint4 w = *reinterpret_cast<const uint4*>(src + i);
+          const uint4 w = *reinterpret_cast<const uint4*>(src + (((i / VEC) ^ key) * VEC));
           const T* wv = reinterpret_cast<const T*>(&w);
 #pragma unroll
           for (int k = 0; k < VEC; ++k) v[i + k] = wv[k];
