@@ -108,6 +108,14 @@ struct Walker {
 
 int sm_count();
 
+// Development knob "<warps per CTA>x<CTAs per SM>" from the environment (e.g. VCFB_ENC_CFG=5x2)
+// as the integer 10*warps + ctas; 0 when unset or malformed.
+inline int dev_cfg(const char* name) {
+  const char* e = getenv(name);
+  if (!e || e[0] < '1' || e[0] > '9' || e[1] != 'x' || e[2] < '1' || e[2] > '9' || e[3] != 0) return 0;
+  return (e[0] - '0') * 10 + (e[2] - '0');
+}
+
 }  // namespace fast
 
 // packed (f32x2) exact encoder, compiled in its own translation unit with -fmad=false

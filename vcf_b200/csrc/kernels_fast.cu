@@ -697,16 +697,11 @@ int launch_encode_fast(const EncArgs& a, int B, cudaStream_t s) {
     }
 
   const bool exact = !(a.flags & VCFB_F_CONTRACT);
-  // tuning knob (development only): VCFB_ENC_CFG = "<warps per CTA>x<CTAs per SM>"
-  int cfg = 42;
-  if (const char* e = getenv("VCFB_ENC_CFG")) cfg = (e[0] - '0') * 10 + (e[2] - '0');
-  switch (cfg) {
-    case 25: return launch_enc_t<2, 5>(exact, a.q_pow2, in_map, out_map, fa, s);
-    case 33: return launch_enc_t<3, 3>(exact, a.q_pow2, in_map, out_map, fa, s);
-    case 19: return launch_enc_t<1, 9>(exact, a.q_pow2, in_map, out_map, fa, s);
+  // development knob VCFB_ENC_CFG: 5x2 reproduces the scheduler imbalance of 5 warps per CTA,
+  // 4x3 the 2-stage ring with 12 warps per SM (both measured slower)
+  switch (dev_cfg("VCFB_ENC_CFG")) {
     case 52: return launch_enc_t<5, 2>(exact, a.q_pow2, in_map, out_map, fa, s);
-    case 43: return launch_encode_packed(43, a.q_pow2, in_map, out_map, fa, s);
-    case 61: return launch_encode_packed(61, a.q_pow2, in_map, out_map, fa, s);
+    case 43: if (exact) return launch_encode_packed(43, a.q_pow2, in_map, out_map, fa, s);   // fallthrough
     default: return launch_enc_t<4, 2>(exact, a.q_pow2, in_map, out_map, fa, s);
   }
 }
@@ -775,13 +770,9 @@ int launch_decode_fast(const DecArgs& a, int B, cudaStream_t s) {
   if (nt > 0x7fffffffLL - (1 << 20)) return VCFB_E_UNSUPP;
   fa.ntiles = int(nt);
   fa.q = a.q_int;
-  int cfg = 0;   // tuning knob (development only): VCFB_DEC_CFG = "<warps per CTA>x<CTAs per SM>"
-  if (const char* e = getenv("VCFB_DEC_CFG")) cfg = (e[0] - '0') * 10 + (e[2] - '0');
   if (a.flags & VCFB_F_FP64) {
-    switch (cfg) {
-      case 16: return launch_dec_t<double, true, 1, 6>(in_map, out_map, fa, s);
-      case 32: return launch_dec_t<double, true, 3, 2>(in_map, out_map, fa, s);
-      case 23: return launch_dec_t<double, true, 2, 3>(in_map, out_map, fa, s);
+    // development knob VCFB_DEC_CFG: 4x1 = the full-tile float64 kernel (4 warps per SM)
+    switch (dev_cfg("VCFB_DEC_CFG")) {
       case 41: return launch_dec_t<double, true, 4, 1>(in_map, out_map, fa, s);
       case 42: return launch_dec_f64h<4, 2>(in_map, out_map, fa, s);
       default: return launch_dec_f64h<8, 1>(in_map, out_map, fa, s);
