@@ -444,3 +444,51 @@ def test_fast_path_statistics(torch_cuda):
             assert int(s["sse"][c]) == O.sse_int(frames[..., c], refd[..., c])
         assert s["nsamples"] == frames.size
         assert s["sumdiff"] == int((frames.astype(np.int64) - refd.astype(np.int64)).sum())
+
+
+def test_no_writes_outside_the_output_arrays(torch_cuda):
+    """compute-sanitizer is closed on this GPU pool, so out-of-bounds writes are hunted with
+    canaries: every output lives inside a 0xAB-filled buffer at an odd offset and the bytes
+    around it must be untouched after each kernel family (general at every B, TMA fast
+    path, colour codecs); results are checked against the oracle as well."""
+    from vcf_b200 import ColorCodec
+    t = torch_cuda
+    PAD = 4096
+
+    def guarded(nbytes, off):
+        buf = t.full((PAD + off + nbytes + PAD,), 0xAB, dtype=t.uint8, device="cuda")
+        return buf, buf[PAD + off:PAD + off + nbytes]
+
+    def intact(buf, nbytes, off):
+        return bool((buf[:PAD + off] == 0xAB).all()) and bool((buf[PAD + off + nbytes:] == 0xAB).all())
+
+    cases = [(8, (2, 16, 128), 0), (8, (1, 40, 1024), 0),              # fast path (aligned by construction)
+             (8, (1, 37, 53), 1), (4, (2, 30, 70), 3), (16, (1, 50, 90), 5), (32, (1, 70, 130), 7),
+             (8, (1, 8, 8), 2), (16, (1, 1, 1), 9)]
+    for B, (n, H, W), off in cases:
+        frames = np.stack([O.synthetic_frame(H, W, 1300 + i, "noise") for i in range(n)])
+        Hp, Wp, _, _ = O.padded_shape(H, W, B)
+        xbuf, xv = guarded(frames.size, off)
+        x = xv.view(n, H, W, 3)
+        x.copy_(t.from_numpy(frames))
+        ibuf, iv = guarded(n * Hp * Wp * 3, off)
+        idx = iv.view(n, Hp, Wp, 3)
+        _codec(block_size=B, q=8).encode(x, out=idx)
+        t.cuda.synchronize()
+        assert intact(ibuf, n * Hp * Wp * 3, off), ("encode", B, H, W, off)
+        ref = np.stack([O.encode_array(f, B, 8) for f in frames])
+        assert np.array_equal(idx.cpu().numpy(), ref)
+        for fp64 in (True, False):
+            ybuf, yv = guarded(frames.size, off)
+            y = yv.view(n, H, W, 3)
+            _codec(block_size=B, q=8, fp64=fp64).decode(idx, (H, W), out=y)
+            t.cuda.synchronize()
+            assert intact(ybuf, frames.size, off), ("decode", B, H, W, off, fp64)
+            if fp64:
+                assert np.array_equal(y.cpu().numpy(), np.stack([O.decode_array(k, (H, W, 3), B, 8) for k in ref]))
+        assert intact(xbuf, frames.size, off)
+    # colour codecs write through plain pointers as well
+    img = t.from_numpy(O.synthetic_frame(33, 71, 5, "noise")).cuda()
+    for color in ("YCoCg", "YCrCb"):
+        k = ColorCodec(color, 7).encode(img)
+        assert k.shape == img.shape
