@@ -184,6 +184,13 @@ struct vcfb_ctx {
   cudaEvent_t ready;
 };
 
+// Pageable user buffers: by default handed to cudaMemcpyAsync as they are (the driver stages
+// them through its own pinned pool); VCFB_STAGE=1 stages explicitly through the slot buffer.
+static bool stage_pageable() {
+  static const bool v = getenv("VCFB_STAGE") != nullptr;
+  return v;
+}
+
 static bool is_pinned(const void* p) {
   if (!p) return false;
   cudaPointerAttributes at;
@@ -319,7 +326,7 @@ int vcfb_encode_host(vcfb_ctx* c, const uint8_t* rgb, int n_frames, int H, int W
   double* d_w; int64_t* d_st;
   rc = aux_prepare(c, weights, w_b, stats != nullptr, &d_w, &d_st);
   if (rc) return rc;
-  const bool pin_in = is_pinned(rgb), pin_out = is_pinned(idx_out);
+  const bool pin_in = is_pinned(rgb) || !stage_pageable(), pin_out = is_pinned(idx_out) || !stage_pageable();
   int cf = int(CHUNK_TARGET / in_f);
   cf = cf < 1 ? 1 : cf;
   if (cf > (n_frames + NSLOT - 1) / NSLOT) cf = (n_frames + NSLOT - 1) / NSLOT;
@@ -367,8 +374,9 @@ int vcfb_decode_host(vcfb_ctx* c, const uint8_t* idx, int n_frames, int H, int W
   double* d_w; int64_t* d_st;
   rc = aux_prepare(c, weights, w_b, stats != nullptr, &d_w, &d_st);
   if (rc) return rc;
-  const bool all_pinned = is_pinned(idx) && (!rgb_out || is_pinned(rgb_out)) && (!y_out || is_pinned(y_out)) &&
-                          (!original || is_pinned(original));
+  const bool all_pinned = !stage_pageable() ||
+                          (is_pinned(idx) && (!rgb_out || is_pinned(rgb_out)) && (!y_out || is_pinned(y_out)) &&
+                           (!original || is_pinned(original)));
   int cf = int(CHUNK_TARGET / idx_f);
   cf = cf < 1 ? 1 : cf;
   if (cf > (n_frames + NSLOT - 1) / NSLOT) cf = (n_frames + NSLOT - 1) / NSLOT;
