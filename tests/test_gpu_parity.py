@@ -492,3 +492,31 @@ def test_no_writes_outside_the_output_arrays(torch_cuda):
     for color in ("YCoCg", "YCrCb"):
         k = ColorCodec(color, 7).encode(img)
         assert k.shape == img.shape
+
+
+@pytest.mark.parametrize("q", [0.5, 2.5, 12.5, 1000, 40000])
+def test_unusual_quantisation_steps(q, torch_cuda):
+    """Steps the reference's CLI would not produce but its arithmetic defines: fractional
+    (numpy divides by a float, decodes in float64 without the int16 product), sub-unit powers
+    of two (massive uint8 wrap), and steps whose int16 product q*k wraps (src/2D-DCT.py:410
+    keeps int16)."""
+    t = torch_cuda
+    for B, (H, W) in ((8, (64, 256)), (8, (40, 72)), (16, (48, 80))):
+        img = O.synthetic_frame(H, W, 1400 + B, "natural")
+        x = t.from_numpy(img).cuda()
+        for fp64, dt in ((False, np.float32), (True, np.float64)):
+            ref = O.encode_array(img, B, q, dtype=dt)
+            got = _codec(block_size=B, q=q, fp64=fp64).encode(x)
+            assert np.array_equal(got.cpu().numpy(), ref), (B, H, W, q, fp64)
+        idx = np.random.default_rng(int(q * 2)).integers(0, 256, size=ref.shape, dtype=np.uint8)
+        if q >= 32768:      # the reference's int16 dequantiser raises; so does the library
+            from vcf_b200 import VcfbError
+            with pytest.raises(OverflowError):
+                O.decode_array(idx, img.shape, B, q)
+            with pytest.raises(VcfbError):
+                _codec(block_size=B, q=q, fp64=True).decode(t.from_numpy(idx).cuda(), (H, W))
+            continue
+        with np.errstate(over="ignore", invalid="ignore"):
+            refd = O.decode_array(idx, img.shape, B, q)
+        got = _codec(block_size=B, q=q, fp64=True).decode(t.from_numpy(idx).cuda(), (H, W))
+        assert np.array_equal(got.cpu().numpy(), refd), (B, H, W, q)

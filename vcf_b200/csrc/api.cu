@@ -114,6 +114,11 @@ int vcfb_decode_dev(const uint8_t* idx, int n_frames, int H, int W, int B, doubl
   int rc = check_common(idx, n_frames, H, W, B, q, color, flags, weights, &a.g);
   if (rc) return rc;
   if (!rgb_out && !y_out && !(original && stats)) { set_error("decode has no output"); return VCFB_E_ARG; }
+  if (q == floor(q) && q >= 32768.0) {
+    // numpy refuses `python int * int16 array` when the int does not fit int16 (src/2D-DCT.py:410)
+    set_error("integral quantisation step does not fit int16: the reference's dequantiser raises OverflowError");
+    return VCFB_E_ARG;
+  }
   a.idx = idx;
   a.rgb = rgb_out;
   a.y_out = y_out;
