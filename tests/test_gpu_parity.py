@@ -297,6 +297,90 @@ def test_fast_decode_path(q, torch_cuda):
     assert np.array_equal(got.cpu().numpy(), O.decode_array(idx, img.shape, 8, 300))
 
 
+def _crafted_indices(rng, H, W, kind):
+    """Index arrays (subband layout, B=8) that steer the two-tier decoder into each of its
+    branches: DC-only half-tiles, DC-only blocks next to dense ones, sparse +-1 indices whose
+    colour mix cancels (exact integers in R, G or B although Y/Co/Cg carry AC terms)."""
+    ny, nx = H // 8, W // 8
+    k = np.zeros((ny, nx, 8, 8, 3), dtype=np.int64)            # [block y, block x, u, i, c]
+    k[:, :, 0, 0, :] = rng.integers(-40, 41, size=(ny, nx, 3))
+    if kind == "dc":
+        pass
+    elif kind == "dc_extreme":
+        k[:, :, 0, 0, :] = rng.choice([-128, -127, 0, 126, 127], size=(ny, nx, 3))
+    elif kind == "mixed":
+        dense = rng.random((ny, nx)) < 0.15
+        k[dense] = rng.integers(-6, 7, size=(int(dense.sum()), 8, 8, 3))
+        sparse = (rng.random((ny, nx)) < 0.5) & ~dense
+        n = int(sparse.sum())
+        ks = np.zeros((n, 8, 8, 3), dtype=np.int64)
+        ks[:, 0, 0, :] = rng.integers(-40, 41, size=(n, 3))
+        u, i = rng.integers(0, 3, size=n), rng.integers(0, 3, size=n)
+        pat = rng.integers(0, 4, size=n)
+        for j in range(n):
+            v = int(rng.integers(1, 3))
+            if pat[j] == 0:      # Y and Cg equal: R and B planes lose the term, G keeps it
+                ks[j, u[j], i[j], 0] = v; ks[j, u[j], i[j], 2] = v
+            elif pat[j] == 1:    # Co only: G = Y + Cg stays DC-only
+                ks[j, u[j], i[j], 1] = v
+            elif pat[j] == 2:    # Y = -Cg: G plane DC-only
+                ks[j, u[j], i[j], 0] = v; ks[j, u[j], i[j], 2] = -v
+            else:                # rational positions only
+                ks[j, 4, 0, 0] = v; ks[j, 0, 4, 1] = -v; ks[j, 4, 4, 2] = v
+        k[sparse] = ks
+    elif kind == "rowwise":
+        # long DC-only runs interrupted by single dense blocks: partially DC-only half-tiles
+        hit = rng.random((ny, nx)) < 0.04
+        k[hit] = rng.integers(-3, 4, size=(int(hit.sum()), 8, 8, 3))
+    sub = k.transpose(2, 0, 3, 1, 4).reshape(H, W, 3)           # sub[j*ny+y, i*nx+x, c]
+    return (sub + 128).astype(np.uint8)
+
+
+@pytest.mark.parametrize("cfg", ["8x1", "9x1", "4x3"], ids=["two_tier", "exact_dcskip", "two_tier_12warps"])
+@pytest.mark.parametrize("kind", ["dc", "dc_extreme", "mixed", "rowwise"])
+def test_two_tier_decode_branches(kind, cfg, torch_cuda, monkeypatch):
+    """Every branch of kernels_dec2t.cu (and the DC-only shortcut of the exact kernel) against the
+    oracle's float64 chain, bit for bit.  The decoder is forced: at these sizes the library would
+    not probe and would use the plain exact kernel."""
+    from vcf_b200 import _lib
+    t = torch_cuda
+    monkeypatch.setenv("VCFB_DEC_CFG", cfg)
+    rng = np.random.default_rng(len(kind))
+    for (H, W) in ((64, 256), (120, 640)):
+        for q in (1, 3, 8, 12, 16, 31, 32, 64, 255):
+            idx = _crafted_indices(rng, H, W, kind)
+            ref = O.decode_array(idx, (H, W, 3), 8, q)
+            got = _codec(block_size=8, q=q, fp64=True).decode(t.from_numpy(idx).cuda(), (H, W))
+            assert _lib.last_kernel() == "dec8_fast"
+            bad = int((got.cpu().numpy() != ref).sum())
+            assert bad == 0, (kind, H, W, q, bad)
+
+
+def test_float64_decoders_agree_full_size(torch_cuda, monkeypatch):
+    """4K frames, natural and noise content, q from dense to DC-only indices: the probed default
+    (device-side choice), the two-tier decoder and the exact kernel with the DC-only shortcut
+    against the plain exact kernel (itself checked against the oracle), whole batch."""
+    t = torch_cuda
+    H, W = 2160, 3840
+    frames = np.stack([O.synthetic_frame(H, W, 40 + i, "noise" if i == 2 else "natural") for i in range(3)])
+    for x in (t.from_numpy(frames).cuda(), t.from_numpy(frames[2:]).cuda(), t.from_numpy(frames[:1]).cuda()):
+        for q in (2, 5, 8, 12, 16, 24, 32, 48, 64):
+            idx = _codec(block_size=8, q=q).encode(x)
+            monkeypatch.setenv("VCFB_DEC_CFG", "9x2")
+            ref = _codec(block_size=8, q=q, fp64=True).decode(idx, (H, W))
+            for cfg in (None, "8x1", "9x1"):
+                if cfg:
+                    monkeypatch.setenv("VCFB_DEC_CFG", cfg)
+                else:
+                    monkeypatch.delenv("VCFB_DEC_CFG")
+                got = _codec(block_size=8, q=q, fp64=True).decode(idx, (H, W))
+                assert bool(t.equal(got, ref)), (q, cfg, int((got != ref).sum().item()))
+            if q == 16 and x.shape[0] == 3:
+                refd = O.decode_array(idx[0].cpu().numpy(), (H, W, 3), 8, q)
+                assert np.array_equal(ref[0].cpu().numpy(), refd)
+        monkeypatch.delenv("VCFB_DEC_CFG", raising=False)
+
+
 @pytest.mark.parametrize("color", ["YCoCg", "YCrCb"])
 def test_standalone_colour_codecs(color, torch_cuda, golden_dir):
     """src/YCoCg.py:33-85 and src/YCrCb.py:33-69 as codecs of their own (SURVEY 8a rows A11,

@@ -104,3 +104,19 @@ def test_stats_helpers():
     assert O.entropy_bits(hist[0]) <= 8 * idx[..., 0].size
     dec = O.decode_array(idx, img.shape, 8, 32)
     assert abs(float(O.rmse(img, dec)) - np.sqrt(O.sse_int(img, dec) / img.size)) < 1e-4
+
+
+def test_dc_only_block_chain():
+    """kernels_dec2t.cu evaluates blocks without AC indices as  (X * c0) * c0  with c0 =
+    pocketfft's sqrt(2) constant (every other operand of the DAG is an exact zero).  Pinned
+    here against the real scipy.fftpack: all 64 samples of idct2(DC-only block) are bitwise
+    equal to that product, scaled by the exact 2^-4."""
+    import scipy.fftpack as sf
+    c0 = float.fromhex("0x1.6a09e667f3bcdp+0")
+    rng = np.random.default_rng(3)
+    xs = np.concatenate([rng.integers(-32768, 32768, size=4000), np.arange(-300, 301)]).astype(np.float64)
+    blocks = np.zeros((xs.size, 8, 8))
+    blocks[:, 0, 0] = xs
+    got = sf.idct(sf.idct(blocks, norm="ortho", axis=1), norm="ortho", axis=2)
+    want = (xs * c0) * c0 * 0.0625
+    assert np.array_equal(got, np.broadcast_to(want[:, None, None], got.shape))

@@ -50,7 +50,15 @@ struct FastArgs {
 struct FastDecArgs {
   int ntiles, tiles_x, ny, top;
   int q;
+  // Device-side dispatch between the three float64 decoders (kernels_fast.cu "probe"): when
+  // `choice` is set, the kernel runs only if *choice == kind and exits at once otherwise.
+  const int* choice;
+  int kind;
 };
+enum { DEC_EXACT = 0, DEC_EXACT_DCSKIP = 1, DEC_TWO_TIER = 2 };
+__device__ __forceinline__ bool not_chosen(const FastDecArgs& a) {
+  return a.choice != nullptr && *reinterpret_cast<const volatile int*>(a.choice) != a.kind;
+}
 
 __host__ __device__ constexpr double p2(int e) {
   double r = 1.0;
@@ -121,5 +129,9 @@ inline int dev_cfg(const char* name) {
 // packed (f32x2) exact encoder, compiled in its own translation unit with -fmad=false
 int launch_encode_packed(int nwarps_cfg, bool qpow2, const CUtensorMap& in_map, const CUtensorMap& out_map,
                          const fast::FastArgs& fa, cudaStream_t s);
+
+// two-tier float64 decoder (kernels_dec2t.cu)
+int launch_decode_2t(int cfg, const CUtensorMap& in_map, const CUtensorMap& out_map, const fast::FastDecArgs& fa,
+                     cudaStream_t s);
 
 }  // namespace vcfb

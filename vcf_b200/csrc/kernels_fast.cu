@@ -19,7 +19,10 @@
 //     otherwise), truncation, bias + wrap, and 12 bytes per (u,i) go out as three
 //     32-bit words into the dense TMA store box [j][i][block*3+c];
 //   * every shared-memory offset is a compile-time immediate on a per-thread base.
+#include <mutex>
+
 #include "fast_common.cuh"
+#include "dec8_dc.cuh"
 
 namespace vcfb {
 
@@ -251,8 +254,6 @@ template <typename T> __device__ __forceinline__ int trunc_to_int(T x);
 template <> __device__ __forceinline__ int trunc_to_int<float>(float x) { return __float2int_rz(x); }
 template <> __device__ __forceinline__ int trunc_to_int<double>(double x) { return __double2int_rz(x); }
 
-__device__ __forceinline__ int clamp255(int v) { return min(max(v, 0), 255); }
-
 template <typename T> struct Vec;   // 16-byte vector of T
 template <> struct Vec<float> { using type = float4; static constexpr int N = 4; };
 template <> struct Vec<double> { using type = double2; static constexpr int N = 2; };
@@ -446,13 +447,14 @@ constexpr int H64_F_BYTES = 3 * 8 * H64_PP * 8;
 constexpr int H64_WARP_SMEM = 26240;
 static_assert(NSTAGE * TILE + H64_F_BYTES + 8 * NSTAGE <= H64_WARP_SMEM, "decode f64 half-tile smem");
 
-template <bool EXACT, int NWARPS, int CTAS>
+template <bool EXACT, int NWARPS, int CTAS, bool DCSKIP>
 __global__ void __launch_bounds__(NWARPS * 32, CTAS)
 dec8_f64h_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
                  const FastDecArgs a) {
   using T = double;
   using O = Ops<double, EXACT>;
   extern __shared__ __align__(128) unsigned char smem[];
+  if (not_chosen(a)) return;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   unsigned char* ring = smem + warp * H64_WARP_SMEM;
   T* F = reinterpret_cast<T*>(ring + NSTAGE * TILE);
@@ -501,6 +503,9 @@ dec8_f64h_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_consta
   const int woff = (6 * G1) >> 2;              // word of the first byte of the lane's 6-byte run
   const int sh0 = ((6 * G1) & 3) * 8;          // bit offset inside that word (0 or 16)
   constexpr T SCALE = T(p2(2 * M8I::exp(0)));
+  Lane L;
+  L.i1 = i1; L.G1 = G1; L.G2 = G2; L.y2 = y2; L.sh0 = sh0; L.q = q;
+  const uint32_t dcm = i1 == 0 ? 0u : 0xffffffffu;     // row 0 of column 0 holds the DC indices
 
   int k = 0;
   for (int tile = w.tile; tile < w.ntiles; tile += w.stride, ++k) {
@@ -520,7 +525,27 @@ dec8_f64h_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_consta
         }
     }
     __syncwarp();
-
+    // A tile without any AC index (smooth content at a coarse step): two multiplications per
+    // block and channel instead of the transform (dec8_dc.cuh).
+    bool dc_tile = false;
+    if (DCSKIP) {
+      uint32_t nz0 = ((wd[0][0][0] ^ 0x80808080u) | (wd[1][0][0] ^ 0x80808080u)) & dcm;
+      uint32_t nz1 = ((wd[0][0][1] ^ 0x80808080u) | (wd[1][0][1] ^ 0x80808080u)) & dcm;
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int uu = 1; uu < 8; ++uu) {
+          nz0 |= wd[h][uu][0] ^ 0x80808080u;
+          nz1 |= wd[h][uu][1] ^ 0x80808080u;
+        }
+      const uint32_t lo = __funnelshift_r(nz0, nz1, sh0), hi = (nz1 >> sh0) & 0xffffu;
+      dc_tile = !__any_sync(0xffffffffu, (lo | hi) != 0u);
+    }
+    if (dc_tile) {
+      dc_blocks(L, wd[0][0][0], wd[0][0][1], tb, 0, 0xffu);
+      dc_blocks(L, wd[1][0][0], wd[1][0][1], tb, 1, 0xffu);
+      __syncwarp();
+    } else {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       // ---- pass 1: dequantise + inverse DCT over u, 2 blocks per lane and channel ------
@@ -585,6 +610,7 @@ dec8_f64h_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_consta
         orow[2] = make_uint4(ww[8], ww[9], ww[10], ww[11]);
       }
       __syncwarp();
+    }
     }
     tma::fence_proxy_async();
     __syncwarp();
@@ -723,13 +749,13 @@ static int launch_dec_t(const CUtensorMap& in_map, const CUtensorMap& out_map, c
   return VCFB_OK;
 }
 
-template <int NWARPS, int CTAS>
+template <int NWARPS, int CTAS, bool DCSKIP = true>
 static int launch_dec_f64h(const CUtensorMap& in_map, const CUtensorMap& out_map, const FastDecArgs& fa,
                            cudaStream_t s) {
   int grid = sm_count() * CTAS;
   const int need = (fa.ntiles + NWARPS - 1) / NWARPS;
   if (grid > need) grid = need;
-  auto kern = dec8_f64h_kernel<true, NWARPS, CTAS>;
+  auto kern = dec8_f64h_kernel<true, NWARPS, CTAS, DCSKIP>;
   const int smem_bytes = NWARPS * H64_WARP_SMEM;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dec8_f64h)");
@@ -738,6 +764,153 @@ static int launch_dec_f64h(const CUtensorMap& in_map, const CUtensorMap& out_map
   e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "dec8_f64h_kernel launch");
   return VCFB_OK;
+}
+
+
+// ---- probe: which float64 decoder suits this batch ------------------------------------------
+// All three decoders give identical bytes; they differ in speed by content:
+//   * exact chain (dec8_f64h_kernel): the reference's operation sequence for every sample;
+//   * the same with the DC-only tile shortcut: pays ~4 % on tiles that have AC indices, wins
+//     3.7x on tiles that have none (smooth content at a coarse step);
+//   * two-tier (kernels_dec2t.cu): 27 % faster when exact-integer samples are rare, i.e. when
+//     the indices are dense; up to 1.8x slower when they are sparse (+-1 indices that cancel).
+// One CTA reads 256 tiles spread over the batch, counts DC-only tiles and non-zero AC indices,
+// and writes its choice to a slot in device memory; the three kernels are launched behind it and
+// the two that were not chosen return at once.  Correctness never depends on the choice.
+constexpr int PROBE_TILES = 256;
+constexpr int PROBE_CTAS = 32;             // x 8 warps x 1 tile
+constexpr int PROBE_MIN_TILES = 4096;      // smaller jobs: not worth three extra launches
+
+struct ProbeSlot {
+  int sparse, dc_tiles, ticket, choice;    // the first three are zero between launches
+};
+
+struct ProbeArgs {
+  const uint8_t* idx;
+  long long frame_bytes;       // Hp * Wp * 3
+  int row_bytes;               // Wp * 3
+  int ny, nx, tiles_x, per_frame, ntiles;
+  ProbeSlot* slot;
+};
+
+__device__ __forceinline__ uint32_t nonzero_flags(uint32_t x) {      // 0x80 in every byte of x that is not 0x80
+  const uint32_t y = x ^ 0x80808080u;
+  return (y | ((y & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u;
+}
+
+// Counts, per sampled tile, the non-zero AC indices of each of its 16 blocks (all channels).
+// A block with 1..6 of them is "sparse": the kind whose samples land on exact integers.
+__global__ void __launch_bounds__(256, 1) dec8_probe_kernel(const ProbeArgs a) {
+  __shared__ int s_sparse, s_dc;
+  if (threadIdx.x == 0) {
+    s_sparse = 0;
+    s_dc = 0;
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int step = a.ntiles / PROBE_TILES;
+  int nsparse = 0, ndc = 0;
+  for (int sidx = blockIdx.x * 8 + warp; sidx < PROBE_TILES; sidx += PROBE_CTAS * 8) {
+    const int t = sidx * step + (sidx * 7) % step;
+    const int f = t / a.per_frame, rem = t - f * a.per_frame;
+    const int by = rem / a.tiles_x, tx = rem - by * a.tiles_x;
+    uint32_t acc[4] = {0u, 0u, 0u, 0u};        // 16 byte-wide counters: block b in byte b & 3 of acc[b >> 2]
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int seg = lane + 32 * r, j = seg >> 3, i = seg & 7;          // subband (j, i): 16 blocks x 3 bytes
+      const uint4* p = reinterpret_cast<const uint4*>(a.idx + f * a.frame_bytes + (long long)(j * a.ny + by) * a.row_bytes +
+                                                      (i * a.nx + tx * 16) * 3);
+      const uint4 v0 = __ldg(p), v1 = __ldg(p + 1), v2 = __ldg(p + 2);
+      const uint32_t w[12] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w};
+      if (seg != 0) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {           // 3 words = 4 blocks
+          const uint32_t f0 = nonzero_flags(w[3 * g]), f1 = nonzero_flags(w[3 * g + 1]), f2 = nonzero_flags(w[3 * g + 2]);
+          const uint32_t c0 = __popc(f0 & 0x00808080u);
+          const uint32_t c1 = __popc(f0 & 0x80000000u) + __popc(f1 & 0x00008080u);
+          const uint32_t c2 = __popc(f1 & 0x80800000u) + __popc(f2 & 0x00000080u);
+          const uint32_t c3 = __popc(f2 & 0x80808000u);
+          acc[g] += c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);          // <= 3 per segment, 189 per tile: no carry
+        }
+      }
+    }
+#pragma unroll
+    for (int g = 0; g < 4; ++g) acc[g] = __reduce_add_sync(0xffffffffu, acc[g]);
+    const uint32_t mine = lane < 16 ? (acc[lane >> 2] >> (8 * (lane & 3))) & 0xffu : 0xffu;
+    nsparse += __popc(__ballot_sync(0xffffffffu, mine >= 1u && mine <= 6u));
+    ndc += (acc[0] | acc[1] | acc[2] | acc[3]) == 0u;
+  }
+  if (lane == 0) {
+    atomicAdd(&s_sparse, nsparse);
+    atomicAdd(&s_dc, ndc);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ProbeSlot* sl = a.slot;
+    atomicAdd(&sl->sparse, s_sparse);
+    atomicAdd(&sl->dc_tiles, s_dc);
+    __threadfence();
+    if (atomicAdd(&sl->ticket, 1) == PROBE_CTAS - 1) {      // last CTA: decide, and leave the slot clean
+      __threadfence();
+      const int sparse = atomicExch(&sl->sparse, 0), dc = atomicExch(&sl->dc_tiles, 0);
+      int kind = DEC_EXACT;
+      if (50 * sparse <= PROBE_TILES * 16) kind = DEC_TWO_TIER;         // <= 2 % sparse blocks
+      else if (16 * dc > PROBE_TILES) kind = DEC_EXACT_DCSKIP;          // > 1/16 of the tiles DC-only
+      sl->choice = kind;
+      sl->ticket = 0;
+    }
+  }
+}
+
+// Slots for the probe's answer: one small ring per device, allocated on first use and kept for
+// the life of the process; concurrent launches (other streams, other threads) get distinct slots.
+static ProbeSlot* probe_slot() {
+  constexpr int NSLOT = 4096, MAXDEV = 64;
+  static std::mutex mu;
+  static ProbeSlot* ring[MAXDEV] = {};
+  static unsigned next[MAXDEV] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAXDEV) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  if (!ring[dev]) {
+    if (cudaMalloc(&ring[dev], NSLOT * sizeof(ProbeSlot)) != cudaSuccess ||
+        cudaMemset(ring[dev], 0, NSLOT * sizeof(ProbeSlot)) != cudaSuccess ||
+        cudaStreamSynchronize(0) != cudaSuccess) {       // once per device: the zeros are there before any probe
+      cudaGetLastError();
+      ring[dev] = nullptr;
+      return nullptr;
+    }
+  }
+  return ring[dev] + (next[dev]++ % NSLOT);
+}
+
+static int launch_decode_f64_probed(const DecArgs& a, const CUtensorMap& in_map, const CUtensorMap& out_map, FastDecArgs fa,
+                             cudaStream_t s) {
+  ProbeSlot* slot = fa.ntiles >= PROBE_MIN_TILES ? probe_slot() : nullptr;
+  if (!slot) return launch_dec_f64h<8, 1, false>(in_map, out_map, fa, s);
+  const Geom& g = a.g;
+  ProbeArgs pa;
+  pa.idx = a.idx;
+  pa.frame_bytes = (long long)g.Hp * g.Wp * 3;
+  pa.row_bytes = g.Wp * 3;
+  pa.ny = g.ny;
+  pa.nx = g.nx;
+  pa.tiles_x = fa.tiles_x;
+  pa.per_frame = g.ny * fa.tiles_x;
+  pa.ntiles = fa.ntiles;
+  pa.slot = slot;
+  dec8_probe_kernel<<<PROBE_CTAS, 256, 0, s>>>(pa);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "dec8_probe_kernel launch");
+  fa.choice = &slot->choice;
+  fa.kind = DEC_EXACT;
+  int rc = launch_dec_f64h<8, 1, false>(in_map, out_map, fa, s);
+  if (rc) return rc;
+  fa.kind = DEC_EXACT_DCSKIP;
+  rc = launch_dec_f64h<8, 1, true>(in_map, out_map, fa, s);
+  if (rc) return rc;
+  fa.kind = DEC_TWO_TIER;
+  return launch_decode_2t(0, in_map, out_map, fa, s);
 }
 
 int launch_decode_fast(const DecArgs& a, int B, cudaStream_t s) {
@@ -770,12 +943,19 @@ int launch_decode_fast(const DecArgs& a, int B, cudaStream_t s) {
   if (nt > 0x7fffffffLL - (1 << 20)) return VCFB_E_UNSUPP;
   fa.ntiles = int(nt);
   fa.q = a.q_int;
+  fa.choice = nullptr;
+  fa.kind = 0;
   if (a.flags & VCFB_F_FP64) {
-    // development knob VCFB_DEC_CFG: 4x1 = the full-tile float64 kernel (4 warps per SM)
-    switch (dev_cfg("VCFB_DEC_CFG")) {
+    // default: probe + device-side choice between the three float64 decoders.  Development knob
+    // VCFB_DEC_CFG forces one: 9x2 exact chain, 9x1 exact chain + DC-only shortcut, 8x1 (and the
+    // other shapes of kernels_dec2t.cu) two-tier, 4x1 the full-tile exact kernel (4 warps per SM)
+    const int cfg = dev_cfg("VCFB_DEC_CFG");
+    switch (cfg) {
+      case 0: return launch_decode_f64_probed(a, in_map, out_map, fa, s);
       case 41: return launch_dec_t<double, true, 4, 1>(in_map, out_map, fa, s);
-      case 42: return launch_dec_f64h<4, 2>(in_map, out_map, fa, s);
-      default: return launch_dec_f64h<8, 1>(in_map, out_map, fa, s);
+      case 91: return launch_dec_f64h<8, 1, true>(in_map, out_map, fa, s);
+      case 92: return launch_dec_f64h<8, 1, false>(in_map, out_map, fa, s);
+      default: return launch_decode_2t(cfg, in_map, out_map, fa, s);
     }
   }
   if (a.flags & VCFB_F_CONTRACT) return launch_dec_t<float, false, 4, 2>(in_map, out_map, fa, s);
