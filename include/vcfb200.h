@@ -87,6 +87,11 @@ const char* vcfb_last_error(void);
  * code path served a request. */
 const char* vcfb_last_kernel(void);
 
+/* Kernels launched so far by the calling thread through this library (monotonic).  The probed
+ * float64 decode of the B=8 fast path counts 4: the probe and three decoders, two of which
+ * return at once. */
+long long vcfb_launch_count(void);
+
 /* Number of CUDA devices visible (0 if none / no driver). */
 int vcfb_device_count(void);
 

@@ -41,6 +41,7 @@ def lib():
     L.vcfb_last_error.restype = C.c_char_p
     L.vcfb_device_count.restype = i
     L.vcfb_last_kernel.restype = C.c_char_p
+    L.vcfb_launch_count.restype = C.c_longlong
     L.vcfb_padded_dims.argtypes = [i, i, i] + [C.POINTER(i)] * 4
     L.vcfb_padded_dims.restype = i
     L.vcfb_encode_dev.argtypes = [vp, i, i, i, i, d, i, u, vp, vp, vp, vp]
@@ -82,6 +83,11 @@ def padded_dims(H: int, W: int, B: int):
     a = [C.c_int() for _ in range(4)]
     check(lib().vcfb_padded_dims(H, W, B, *[C.byref(x) for x in a]))
     return tuple(x.value for x in a)
+
+
+def launch_count() -> int:
+    """Kernels launched so far by the calling thread (vcfb_launch_count)."""
+    return int(lib().vcfb_launch_count())
 
 
 def last_kernel() -> str:

@@ -15,7 +15,12 @@ static thread_local std::string g_err;
 static thread_local const char* g_kernel = "";
 
 void set_error(const std::string& msg) { g_err = msg; }
-void note_kernel(const char* name) { g_kernel = name; }
+static thread_local long long g_launches = 0;
+void note_kernel(const char* name) {
+  g_kernel = name;
+  ++g_launches;
+}
+void note_extra_launches(int n) { g_launches += n; }
 
 int cuda_fail(cudaError_t e, const char* what) {
   g_err = std::string(what) + ": " + cudaGetErrorString(e);
@@ -60,6 +65,8 @@ int vcfb_version(void) { return VCFB_VERSION; }
 const char* vcfb_last_error(void) { return g_err.c_str(); }
 
 const char* vcfb_last_kernel(void) { return g_kernel; }
+
+long long vcfb_launch_count(void) { return g_launches; }
 
 int vcfb_device_count(void) {
   int n = 0;

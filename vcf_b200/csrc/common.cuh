@@ -48,7 +48,8 @@ struct DecArgs {
 
 void set_error(const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what);
-void note_kernel(const char* name);   // remembered per thread for vcfb_last_kernel()
+void note_kernel(const char* name);   // remembered per thread for vcfb_last_kernel(); counts one launch
+void note_extra_launches(int n);      // launches that do not go through note_kernel()
 
 // general kernels (all B, float32 / float64): kernels_general.cu
 int launch_encode_general(const EncArgs& a, int B, cudaStream_t s);

@@ -902,6 +902,7 @@ static int launch_decode_f64_probed(const DecArgs& a, const CUtensorMap& in_map,
   dec8_probe_kernel<<<PROBE_CTAS, 256, 0, s>>>(pa);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "dec8_probe_kernel launch");
+  note_extra_launches(1);
   fa.choice = &slot->choice;
   fa.kind = DEC_EXACT;
   int rc = launch_dec_f64h<8, 1, false>(in_map, out_map, fa, s);

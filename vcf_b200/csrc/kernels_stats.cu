@@ -143,6 +143,7 @@ int launch_index_stats(const uint8_t* idx, long long n_bytes, bool hist, unsigne
   if (hist) index_stats_kernel<true><<<stats_grid(n_vec), 256, 0, s>>>(reinterpret_cast<const uint4*>(idx), n_vec, stats);
   else index_stats_kernel<false><<<stats_grid(n_vec), 256, 0, s>>>(reinterpret_cast<const uint4*>(idx), n_vec, stats);
   add_counts_kernel<<<1, 1, 0, s>>>(stats, VCFB_STAT_NINDICES, (unsigned long long)n_bytes);
+  note_extra_launches(2);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? VCFB_OK : cuda_fail(e, "index_stats_kernel launch");
 }
@@ -155,6 +156,7 @@ int launch_sse(const uint8_t* a, const uint8_t* b, long long n_bytes, unsigned l
   sse_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const uint4*>(a), reinterpret_cast<const uint4*>(b), n_vec,
                                               stats);
   add_counts_kernel<<<1, 1, 0, s>>>(stats, VCFB_STAT_NSAMPLES, (unsigned long long)n_bytes);
+  note_extra_launches(2);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? VCFB_OK : cuda_fail(e, "sse_kernel launch");
 }
