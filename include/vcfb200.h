@@ -143,6 +143,20 @@ int vcfb_color_encode_dev(const uint8_t* rgb, long long n_pixels, double q, int 
 int vcfb_color_decode_dev(const uint16_t* k, long long n_pixels, double q, int color,
                           uint8_t* rgb_out, void* cuda_stream);
 
+/* Motion estimation of the hybrid codec (src/IPP_DCT.py).
+ *   vcfb_gray_dev         replaces cv2.cvtColor(frame, cv2.COLOR_RGB2GRAY) of
+ *                         src/IPP_DCT.py:350-352 (8-bit fixed point, bit-identical with OpenCV).
+ *   vcfb_block_match_dev  replaces IPP.block_matching's full search (src/IPP_DCT.py:217-244 and
+ *                         :344-373): per bs x bs block the displacement in [-sr, sr]^2 minimising
+ *                         the sum of absolute differences; candidates leaving the frame are
+ *                         skipped, ties go to the first candidate of the dy-major scan.
+ * ref, cur   (n_frames,H,W) uint8 gray frames, device; pair f is matched independently
+ * mv_out     (n_frames, H/bs, W/bs, 2) int16, device: (dx, dy) as the reference stores them
+ * bs in [4, 64], sr in [0, 31], H >= bs, W >= bs. */
+int vcfb_gray_dev(const uint8_t* rgb, long long n_pixels, uint8_t* gray_out, void* cuda_stream);
+int vcfb_block_match_dev(const uint8_t* ref, const uint8_t* cur, int n_frames, int H, int W, int bs, int sr,
+                         int16_t* mv_out, void* cuda_stream);
+
 /* Host-buffer convenience layer (what a numpy caller binds).  A context owns one
  * CUDA stream plus pinned and device staging buffers that grow on demand. */
 typedef struct vcfb_ctx vcfb_ctx;

@@ -165,3 +165,27 @@ def test_batched_iii_driver_equals_per_frame_loop():
         idx = np.load("/tmp/encoded_%04d.npz" % i)["a"]
         assert np.array_equal(idx, O.encode_array(f, 8, 16))
         assert np.array_equal(_read_png("/tmp/decoded_%04d.png" % i), O.decode_array(idx, f.shape, 8, 16))
+
+
+@pytest.mark.gpu
+def test_in_memory_proxy_equals_file_round_trip():
+    """``encode_decode_array`` (no temporary PNGs) gives the hybrid codec the
+    same reconstruction, size and payload files as ``encode_fn`` + ``decode_fn`` through files
+    (the body of src/IPP_DCT.py:595-626)."""
+    img = O.synthetic_frame(72, 136, 90, "natural")
+    _write_png("/tmp/proxy_in.png", img)
+    code = (
+        "import importlib, sys, numpy as np, cv2; sys.argv=['x','encode','-q','12','-t','chain_stub'];"
+        "m = importlib.import_module('2D-DCT-B200'); import parser; c = m.CoDec(parser.parser.parse_known_args()[0]);"
+        "img = cv2.cvtColor(cv2.imread('/tmp/proxy_in.png'), cv2.COLOR_BGR2RGB);"
+        "size_f = c.encode_fn('/tmp/proxy_in.png', '/tmp/proxy_file'); c.decode_fn('/tmp/proxy_file', '/tmp/proxy_file_rec.png');"
+        "rec_f = cv2.cvtColor(cv2.imread('/tmp/proxy_file_rec.png'), cv2.COLOR_BGR2RGB);"
+        "rec_m, size_m = c.encode_decode_array(img, '/tmp/proxy_mem');"
+        "a = np.load('/tmp/proxy_file.npz')['a']; b = np.load('/tmp/proxy_mem.npz')['a'];"
+        "print('SAME', bool(np.array_equal(rec_f, rec_m)), size_f == size_m, bool(np.array_equal(a, b)),"
+        " open('/tmp/proxy_file_shape.bin','rb').read() == open('/tmp/proxy_mem_shape.bin','rb').read())")
+    r = _run(STUB, "-c", code)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "SAME True True True True" in r.stdout, r.stdout[-500:]
+    rec = O.decode_array(O.encode_array(img, 8, 12), img.shape, 8, 12)
+    assert np.array_equal(_read_png("/tmp/proxy_file_rec.png"), rec)

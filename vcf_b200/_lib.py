@@ -69,6 +69,10 @@ def lib():
     L.vcfb_encode_host.restype = i
     L.vcfb_decode_host.argtypes = [vp, vp, i, i, i, i, d, i, u, vp, vp, vp, vp, vp]
     L.vcfb_decode_host.restype = i
+    L.vcfb_gray_dev.argtypes = [vp, ll, vp, vp]
+    L.vcfb_gray_dev.restype = i
+    L.vcfb_block_match_dev.argtypes = [vp, vp, i, i, i, i, i, vp, vp]
+    L.vcfb_block_match_dev.restype = i
     _lib = L
     return L
 

@@ -160,6 +160,22 @@ int vcfb_color_decode_dev(const uint16_t* k, long long n_pixels, double q, int c
   return launch_color_decode(k, n_pixels, q, color, rgb_out, static_cast<cudaStream_t>(cuda_stream));
 }
 
+int vcfb_gray_dev(const uint8_t* rgb, long long n_pixels, uint8_t* gray_out, void* cuda_stream) {
+  if (!rgb || !gray_out) { set_error("NULL pointer"); return VCFB_E_ARG; }
+  if (n_pixels <= 0) { set_error("n_pixels must be > 0"); return VCFB_E_ARG; }
+  return launch_gray(rgb, n_pixels, gray_out, static_cast<cudaStream_t>(cuda_stream));
+}
+
+int vcfb_block_match_dev(const uint8_t* ref, const uint8_t* cur, int n_frames, int H, int W, int bs, int sr,
+                         int16_t* mv_out, void* cuda_stream) {
+  if (!ref || !cur || !mv_out) { set_error("NULL pointer"); return VCFB_E_ARG; }
+  if (n_frames <= 0 || n_frames > 65535) { set_error("n_frames must be in [1, 65535]"); return VCFB_E_ARG; }
+  if (bs < 4 || bs > 64) { set_error("motion block size must be in [4, 64]"); return VCFB_E_ARG; }
+  if (sr < 0 || sr > 31) { set_error("search range must be in [0, 31]"); return VCFB_E_ARG; }
+  if (H < bs || W < bs || H / bs > 65535) { set_error("frame smaller than one motion block (or too tall)"); return VCFB_E_ARG; }
+  return launch_block_match(ref, cur, n_frames, H, W, bs, sr, mv_out, static_cast<cudaStream_t>(cuda_stream));
+}
+
 // ---- host-buffer layer ----------------------------------------------------------
 //
 // A batch is cut into chunks of whole frames; chunk i runs on slot i % NSLOT

@@ -67,4 +67,10 @@ int launch_sse(const uint8_t* a, const uint8_t* b, long long n_bytes, unsigned l
 int launch_color_encode(const uint8_t* rgb, long long npx, double q, int color, uint16_t* out, cudaStream_t s);
 int launch_color_decode(const uint16_t* k, long long npx, double q, int color, uint8_t* rgb, cudaStream_t s);
 
+
+// motion estimation of the hybrid codec (kernels_motion.cu)
+int launch_gray(const uint8_t* rgb, long long npx, uint8_t* gray, cudaStream_t s);
+int launch_block_match(const uint8_t* ref, const uint8_t* cur, int n_frames, int H, int W, int bs, int sr, short* mv,
+                       cudaStream_t s);
+
 }  // namespace vcfb

@@ -1,0 +1,111 @@
+// Row F3 of SURVEY.md section 8: the motion-estimation hot spot of the reference's hybrid
+// codec (src/IPP_DCT.py), the second caller of encode_fn / decode_fn.
+//
+//   gray_kernel          cv2.cvtColor(frame, COLOR_RGB2GRAY) on 8-bit data (src/IPP_DCT.py:350-352):
+//                        OpenCV's fixed point  (R*9798 + G*19235 + B*3735 + 2^14) >> 15
+//   block_match_kernel   full search of src/IPP_DCT.py:217-244 (`_process_block_row`, use_fast =
+//                        False): for every bs x bs block of the current frame the displacement
+//                        (dx, dy) in [-sr, sr]^2 with the smallest sum of absolute differences
+//                        against the reference frame; candidates that leave the frame are skipped
+//                        (:227-233), the scan is dy-major and a later candidate wins only when
+//                        strictly better (:240) -- so ties go to the first candidate in scan order.
+//
+// Integer arithmetic throughout: results are bit-identical with the reference's numpy loop.
+// One CTA per block: the search window and the block sit in shared memory, each thread owns
+// candidates, and the minimum is taken over the key (SAD << 12 | scan index).
+#include "common.cuh"
+
+namespace vcfb {
+namespace {
+
+__global__ void gray_kernel(const uint8_t* __restrict__ rgb, uint8_t* __restrict__ gray, long long npx) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < npx; p += stride) {
+    const unsigned r = rgb[3 * p], g = rgb[3 * p + 1], b = rgb[3 * p + 2];
+    gray[p] = uint8_t((r * 9798u + g * 19235u + b * 3735u + (1u << 14)) >> 15);
+  }
+}
+
+constexpr int ME_THREADS = 256;
+
+__global__ void __launch_bounds__(ME_THREADS)
+block_match_kernel(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ cur, int H, int W, int bs, int sr,
+                   short* __restrict__ mv) {
+  extern __shared__ unsigned char sm[];
+  const int ww = bs + 2 * sr;                 // window side
+  const int wp = ww + 1;                      // pitch
+  unsigned char* win = sm;                    // ww x wp
+  unsigned char* blk = sm + ww * wp;          // bs x bs
+  __shared__ unsigned best_s[ME_THREADS / 32];
+
+  const int bx = blockIdx.x, by = blockIdx.y, f = blockIdx.z;
+  const int i0 = by * bs, j0 = bx * bs;
+  const uint8_t* rf = ref + (size_t)f * H * W;
+  const uint8_t* cf = cur + (size_t)f * H * W;
+  for (int t = threadIdx.x; t < ww * ww; t += ME_THREADS) {
+    const int y = t / ww, x = t - y * ww;
+    const int gy = i0 - sr + y, gx = j0 - sr + x;
+    win[y * wp + x] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? rf[(size_t)gy * W + gx] : 0;
+  }
+  for (int t = threadIdx.x; t < bs * bs; t += ME_THREADS) {
+    const int y = t / bs, x = t - y * bs;
+    blk[t] = cf[(size_t)(i0 + y) * W + j0 + x];
+  }
+  __syncthreads();
+
+  const int nc1 = 2 * sr + 1, ncand = nc1 * nc1;
+  unsigned best = 0xffffffffu;
+  for (int c = threadIdx.x; c < ncand; c += ME_THREADS) {
+    const int dy = c / nc1 - sr, dx = c - (c / nc1) * nc1 - sr;
+    const int ry = i0 + dy, rx = j0 + dx;
+    if (ry < 0 || ry + bs > H || rx < 0 || rx + bs > W) continue;     // src/IPP_DCT.py:227-233
+    const unsigned char* wrow = win + (dy + sr) * wp + (dx + sr);
+    unsigned sad = 0;
+    for (int y = 0; y < bs; ++y) {
+      const unsigned char* a = blk + y * bs;
+      const unsigned char* b = wrow + y * wp;
+#pragma unroll 8
+      for (int x = 0; x < bs; ++x) sad += __sad(int(a[x]), int(b[x]), 0u);
+    }
+    best = min(best, (sad << 12) | unsigned(c));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+  if ((threadIdx.x & 31) == 0) best_s[threadIdx.x >> 5] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int k = 1; k < ME_THREADS / 32; ++k) best = min(best, best_s[k]);
+    const int c = int(best & 0xfffu);
+    // (0,0) is always inside the frame, so `best` is never the empty key
+    short* o = mv + (((size_t)f * gridDim.y + by) * gridDim.x + bx) * 2;
+    o[0] = short(c - (c / nc1) * nc1 - sr);    // dx
+    o[1] = short(c / nc1 - sr);                // dy
+  }
+}
+
+}  // namespace
+
+int launch_gray(const uint8_t* rgb, long long npx, uint8_t* gray, cudaStream_t s) {
+  long long g = (npx + 255) / 256;
+  if (g > 148 * 16) g = 148 * 16;
+  note_kernel("gray");
+  gray_kernel<<<int(g), 256, 0, s>>>(rgb, gray, npx);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "gray_kernel launch");
+  return VCFB_OK;
+}
+
+int launch_block_match(const uint8_t* ref, const uint8_t* cur, int n_frames, int H, int W, int bs, int sr, short* mv,
+                       cudaStream_t s) {
+  const int ww = bs + 2 * sr;
+  const int smem = ww * (ww + 1) + bs * bs;
+  dim3 grid(W / bs, H / bs, n_frames);
+  note_kernel("block_match");
+  block_match_kernel<<<grid, ME_THREADS, smem, s>>>(ref, cur, H, W, bs, sr, mv);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "block_match_kernel launch");
+  return VCFB_OK;
+}
+
+}  // namespace vcfb

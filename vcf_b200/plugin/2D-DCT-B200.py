@@ -140,6 +140,35 @@ class CoDec(CT.CoDec):
     def decode(self, in_fn="/tmp/encoded", out_fn="/tmp/decoded.png"):
         return self.decode_fn(in_fn, out_fn)
 
+    def encode_decode_array(self, img, out_fn):
+        '''In-memory counterpart of the hybrid codec's ``encode_decode_proxy``
+        (src/IPP_DCT.py:595-626): same payload files (``<out_fn><ext>``, ``<out_fn>_shape.bin``)
+        and the same ``(reconstruction, size)`` as ``encode_fn(tmp_png, out_fn)`` followed by
+        ``decode_fn(out_fn, tmp_png)`` -- without the two temporary PNGs and without re-reading
+        the code-stream: the frame goes to the GPU once, the indices come back for the entropy
+        stage, and the reconstruction is decoded from the indices still on the device.  (PNG and
+        the entropy coders are lossless, so the decoder sees the very same indices.)'''
+        import torch
+        img = np.ascontiguousarray(img)
+        self._check_image(img)
+        self.original_shape = img.shape
+        with open(f"{out_fn}_shape.bin", "wb") as file:
+            file.write(struct.pack("iii", *self.original_shape))
+        x = torch.from_numpy(img).cuda()
+        k_dev = self._codec().encode(x)
+        dec = self._codec(decode=True)
+        if getattr(self.args, "filter", "no_filter") == "no_filter":
+            y_dev = dec.decode(k_dev, img.shape[:2])             # overlaps with the entropy stage below
+            decom_k = self.compress(k_dev.cpu().numpy())
+            output_size = self.encode_write_fn(decom_k, out_fn)
+            y = CT.CoDec.filter(self, y_dev.cpu().numpy())
+        else:
+            _, yf = dec.decode(k_dev, img.shape[:2], return_float=True)
+            decom_k = self.compress(k_dev.cpu().numpy())
+            output_size = self.encode_write_fn(decom_k, out_fn)
+            y = np.clip(CT.CoDec.filter(self, yf.cpu().numpy()), 0, 255).astype(np.uint8)
+        return y, output_size
+
     def optimize_block_size(self):
         '''src/2D-DCT.py:533-579 on the GPU: J = rate + Lambda*RMSE per block size, rate =
         bytes of the entropy-coded indices, RMSE as the reference forms it (between the
