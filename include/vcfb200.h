@@ -152,7 +152,7 @@ int vcfb_color_decode_dev(const uint16_t* k, long long n_pixels, double q, int c
  *                         skipped, ties go to the first candidate of the dy-major scan.
  * ref, cur   (n_frames,H,W) uint8 gray frames, device; pair f is matched independently
  * mv_out     (n_frames, H/bs, W/bs, 2) int16, device: (dx, dy) as the reference stores them
- * bs in [4, 64], sr in [0, 31], H >= bs, W >= bs. */
+ * bs a multiple of 4 in [4, 64], sr in [0, 31], H >= bs, W >= bs. */
 int vcfb_gray_dev(const uint8_t* rgb, long long n_pixels, uint8_t* gray_out, void* cuda_stream);
 int vcfb_block_match_dev(const uint8_t* ref, const uint8_t* cur, int n_frames, int H, int W, int bs, int sr,
                          int16_t* mv_out, void* cuda_stream);

@@ -49,5 +49,18 @@ for name, x in (("natural", nat), ("noise", noise)):
             row.append(timed(lambda: dec.decode(idx, (H, W), out=y)))
             outs.append(y.clone() if label in ("probed", "exact old") else None)
         same = bool(torch.equal(outs[0], outs[-1]))
-        print(f"{name:8s} q={q:3d}  " + "  ".join(f"{l}: {v:6.3f}" for (l, _), v in zip(cfgs, row)) + f"  identical={same}")
+        ref = outs[-1]
+        dec32 = Codec(block_size=8, q=q)
+        for label, cfg in (("f32 12w", None), ("f32 8w", "8x1"), ("f32 16w", "4x4"), ("f32 pocketfft", "9x1")):
+            if cfg:
+                os.environ["VCFB_DEC32_CFG"] = cfg
+            else:
+                os.environ.pop("VCFB_DEC32_CFG", None)
+            row.append(timed(lambda: dec32.decode(idx, (H, W), out=y)))
+            if cfg is None:
+                dmax = int((y.to(torch.int16) - ref.to(torch.int16)).abs().max().item())
+                nbad = float((y != ref).float().mean().item())
+        os.environ.pop("VCFB_DEC32_CFG", None)
+        cfgs_all = cfgs + [("f32 12w", 0), ("f32 8w", 0), ("f32 16w", 0), ("f32 pocketfft", 0)]
+        print(f"{name:8s} q={q:3d}  " + "  ".join(f"{l}: {v:6.3f}" for (l, _), v in zip(cfgs_all, row)) + f"  identical={same}  f32: max|d|={dmax} differing={nbad:.2e}")
 os.environ.pop("VCFB_DEC_CFG", None)

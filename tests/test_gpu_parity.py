@@ -381,6 +381,44 @@ def test_float64_decoders_agree_full_size(torch_cuda, monkeypatch):
         monkeypatch.delenv("VCFB_DEC_CFG", raising=False)
 
 
+def test_fast_mode_float32_decoder_tolerances(torch_cuda):
+    """BASELINE north star, fast mode: decoded pixels within +-1 LSB of the reference and PSNR
+    matching to 0.01 dB -- natural, noise and smooth content, dense to DC-only indices, plus
+    arbitrary (non-encoder) index arrays.  (kernels_dec32.cu: scaled AAN transform in float32;
+    blocks without AC indices go through the reference's float64 chain.)"""
+    from vcf_b200 import _lib
+    t = torch_cuda
+    H, W = 1080, 1920
+    yy, xx = np.mgrid[0:H, 0:W]
+    smooth = np.stack([(128 + 100 * np.sin(xx / 300.0 + c) * np.cos(yy / 200.0)).astype(np.uint8) for c in range(3)], -1)
+    frames = {"natural": O.synthetic_frame(H, W, 70, "natural"), "noise": O.synthetic_frame(H, W, 71, "noise"),
+              "smooth": np.ascontiguousarray(smooth)}
+    for name, img in frames.items():
+        for q in (1, 4, 8, 12, 16, 24, 32, 64, 128):
+            idx = O.encode_array(img, 8, q)
+            ref = O.decode_array(idx, img.shape, 8, q)
+            got = _codec(block_size=8, q=q).decode(t.from_numpy(idx).cuda(), (H, W)).cpu().numpy()
+            assert _lib.last_kernel() == "dec8_fast"
+            d = np.abs(got.astype(np.int16) - ref.astype(np.int16))
+            assert d.max() <= 1, (name, q, int(d.max()))
+            p_ref, p_got = O.psnr(img, ref), O.psnr(img, got)
+            assert abs(p_ref - p_got) < 0.01, (name, q, p_ref, p_got, float((d != 0).mean()))
+    rng = np.random.default_rng(9)
+    for q in (3, 32, 255):
+        idx = rng.integers(0, 256, size=(64, 256, 3), dtype=np.uint8)
+        ref = O.decode_array(idx, (64, 256, 3), 8, q)
+        got = _codec(block_size=8, q=q).decode(t.from_numpy(idx).cuda(), (64, 256)).cpu().numpy()
+        assert np.abs(got.astype(np.int16) - ref.astype(np.int16)).max() <= 1, q
+    for kind in ("dc", "dc_extreme", "mixed", "rowwise"):            # exact where it must be: DC-only blocks
+        idx = _crafted_indices(rng, 64, 256, kind)
+        for q in (8, 12, 31, 64):
+            ref = O.decode_array(idx, (64, 256, 3), 8, q)
+            got = _codec(block_size=8, q=q).decode(t.from_numpy(idx).cuda(), (64, 256)).cpu().numpy()
+            assert np.abs(got.astype(np.int16) - ref.astype(np.int16)).max() <= 1, (kind, q)
+            if kind.startswith("dc"):
+                assert np.array_equal(got, ref), (kind, q)
+
+
 @pytest.mark.parametrize("color", ["YCoCg", "YCrCb"])
 def test_standalone_colour_codecs(color, torch_cuda, golden_dir):
     """src/YCoCg.py:33-85 and src/YCrCb.py:33-69 as codecs of their own (SURVEY 8a rows A11,

@@ -170,7 +170,7 @@ int vcfb_block_match_dev(const uint8_t* ref, const uint8_t* cur, int n_frames, i
                          int16_t* mv_out, void* cuda_stream) {
   if (!ref || !cur || !mv_out) { set_error("NULL pointer"); return VCFB_E_ARG; }
   if (n_frames <= 0 || n_frames > 65535) { set_error("n_frames must be in [1, 65535]"); return VCFB_E_ARG; }
-  if (bs < 4 || bs > 64) { set_error("motion block size must be in [4, 64]"); return VCFB_E_ARG; }
+  if (bs < 4 || bs > 64 || (bs & 3)) { set_error("motion block size must be a multiple of 4 in [4, 64]"); return VCFB_E_ARG; }
   if (sr < 0 || sr > 31) { set_error("search range must be in [0, 31]"); return VCFB_E_ARG; }
   if (H < bs || W < bs || H / bs > 65535) { set_error("frame smaller than one motion block (or too tall)"); return VCFB_E_ARG; }
   return launch_block_match(ref, cur, n_frames, H, W, bs, sr, mv_out, static_cast<cudaStream_t>(cuda_stream));

@@ -134,4 +134,8 @@ int launch_encode_packed(int nwarps_cfg, bool qpow2, const CUtensorMap& in_map, 
 int launch_decode_2t(int cfg, const CUtensorMap& in_map, const CUtensorMap& out_map, const fast::FastDecArgs& fa,
                      cudaStream_t s);
 
+// float32 fast-mode decoder (kernels_dec32.cu)
+int launch_decode_f32a(int cfg, const CUtensorMap& in_map, const CUtensorMap& out_map, const fast::FastDecArgs& fa,
+                       cudaStream_t s);
+
 }  // namespace vcfb

@@ -959,8 +959,13 @@ int launch_decode_fast(const DecArgs& a, int B, cudaStream_t s) {
       default: return launch_decode_2t(cfg, in_map, out_map, fa, s);
     }
   }
-  if (a.flags & VCFB_F_CONTRACT) return launch_dec_t<float, false, 4, 2>(in_map, out_map, fa, s);
-  return launch_dec_t<float, true, 4, 2>(in_map, out_map, fa, s);
+  // float32 decode = the fast mode (+-1 LSB): scaled AAN transform + exact DC-only blocks
+  // (kernels_dec32.cu).  Development knob VCFB_DEC32_CFG: 9x1 / 9x2 = the pocketfft codelets in
+  // float32 (individually rounded / contracted), other values = launch shapes of the fast kernel.
+  const int cfg32 = dev_cfg("VCFB_DEC32_CFG");
+  if (cfg32 == 91) return launch_dec_t<float, true, 4, 2>(in_map, out_map, fa, s);
+  if (cfg32 == 92) return launch_dec_t<float, false, 4, 2>(in_map, out_map, fa, s);
+  return launch_decode_f32a(cfg32, in_map, out_map, fa, s);
 }
 
 }  // namespace vcfb

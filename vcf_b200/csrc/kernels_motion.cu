@@ -31,21 +31,21 @@ constexpr int ME_THREADS = 256;
 __global__ void __launch_bounds__(ME_THREADS)
 block_match_kernel(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ cur, int H, int W, int bs, int sr,
                    short* __restrict__ mv) {
-  extern __shared__ unsigned char sm[];
+  extern __shared__ __align__(16) unsigned char sm[];
   const int ww = bs + 2 * sr;                 // window side
-  const int wp = ww + 1;                      // pitch
+  const int wp = (ww + 3 + 4) & ~3;           // pitch: whole words, one spare word for the funnel shift
   unsigned char* win = sm;                    // ww x wp
-  unsigned char* blk = sm + ww * wp;          // bs x bs
+  unsigned char* blk = sm + ww * wp;          // bs x bs (bs is a multiple of 4)
   __shared__ unsigned best_s[ME_THREADS / 32];
 
   const int bx = blockIdx.x, by = blockIdx.y, f = blockIdx.z;
   const int i0 = by * bs, j0 = bx * bs;
   const uint8_t* rf = ref + (size_t)f * H * W;
   const uint8_t* cf = cur + (size_t)f * H * W;
-  for (int t = threadIdx.x; t < ww * ww; t += ME_THREADS) {
-    const int y = t / ww, x = t - y * ww;
+  for (int t = threadIdx.x; t < ww * wp; t += ME_THREADS) {
+    const int y = t / wp, x = t - y * wp;
     const int gy = i0 - sr + y, gx = j0 - sr + x;
-    win[y * wp + x] = (gy >= 0 && gy < H && gx >= 0 && gx < W) ? rf[(size_t)gy * W + gx] : 0;
+    win[t] = (x < ww && gy >= 0 && gy < H && gx >= 0 && gx < W) ? rf[(size_t)gy * W + gx] : 0;
   }
   for (int t = threadIdx.x; t < bs * bs; t += ME_THREADS) {
     const int y = t / bs, x = t - y * bs;
@@ -54,18 +54,25 @@ block_match_kernel(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ 
   __syncthreads();
 
   const int nc1 = 2 * sr + 1, ncand = nc1 * nc1;
+  const int bw = bs >> 2;                     // words per block row
   unsigned best = 0xffffffffu;
   for (int c = threadIdx.x; c < ncand; c += ME_THREADS) {
     const int dy = c / nc1 - sr, dx = c - (c / nc1) * nc1 - sr;
     const int ry = i0 + dy, rx = j0 + dx;
     if (ry < 0 || ry + bs > H || rx < 0 || rx + bs > W) continue;     // src/IPP_DCT.py:227-233
-    const unsigned char* wrow = win + (dy + sr) * wp + (dx + sr);
+    const int off = dx + sr, sh = (off & 3) * 8;
+    const uint32_t* wrow = reinterpret_cast<const uint32_t*>(win + (dy + sr) * wp) + (off >> 2);
+    const uint32_t* brow = reinterpret_cast<const uint32_t*>(blk);
     unsigned sad = 0;
     for (int y = 0; y < bs; ++y) {
-      const unsigned char* a = blk + y * bs;
-      const unsigned char* b = wrow + y * wp;
-#pragma unroll 8
-      for (int x = 0; x < bs; ++x) sad += __sad(int(a[x]), int(b[x]), 0u);
+      uint32_t lo = wrow[0];
+      for (int k = 0; k < bw; ++k) {
+        const uint32_t hi = wrow[k + 1];
+        sad = __vsadu4(brow[k], __funnelshift_r(lo, hi, sh)) + sad;     // 4 pixels per instruction
+        lo = hi;
+      }
+      wrow += wp >> 2;
+      brow += bw;
     }
     best = min(best, (sad << 12) | unsigned(c));
   }
@@ -99,7 +106,7 @@ int launch_gray(const uint8_t* rgb, long long npx, uint8_t* gray, cudaStream_t s
 int launch_block_match(const uint8_t* ref, const uint8_t* cur, int n_frames, int H, int W, int bs, int sr, short* mv,
                        cudaStream_t s) {
   const int ww = bs + 2 * sr;
-  const int smem = ww * (ww + 1) + bs * bs;
+  const int smem = ww * ((ww + 3 + 4) & ~3) + bs * bs;
   dim3 grid(W / bs, H / bs, n_frames);
   note_kernel("block_match");
   block_match_kernel<<<grid, ME_THREADS, smem, s>>>(ref, cur, H, W, bs, sr, mv);
