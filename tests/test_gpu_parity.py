@@ -537,13 +537,15 @@ def test_config4_1080p_sequence_batch(torch_cuda):
 
 
 def test_fast_path_statistics(torch_cuda):
-    """Statistics requested on a fast-path shape: the TMA kernels run, followed by the
-    streaming statistics kernels; every number must equal the oracle's (and the general
-    kernels' for the same input)."""
+    """Statistics requested on a fast-path shape: the TMA kernels run and accumulate the
+    statistics themselves (the histogram and the float32 decoder take the streaming statistics
+    kernels); every number must equal the oracle's."""
     from vcf_b200 import _lib
     from vcf_b200.codec import stats_dict
     t = torch_cuda
-    for (n, H, W, q) in ((3, 64, 256, 16), (1, 1080, 1920, 8)):
+    # (2160x3840 has 8100 tiles: the probed float64 decode; q = 2 -> two-tier, 16 -> exact chain,
+    #  48 -> exact chain with the DC-only shortcut; all with the distortion statistics fused in)
+    for (n, H, W, q) in ((3, 64, 256, 16), (1, 1080, 1920, 8), (1, 2160, 3840, 2), (1, 2160, 3840, 16), (1, 2160, 3840, 48)):
         frames = np.stack([O.synthetic_frame(H, W, 1200 + i, "natural" if i % 2 == 0 else "noise") for i in range(n)])
         x = t.from_numpy(frames).cuda()
         ref = np.stack([O.encode_array(f, 8, q) for f in frames])
@@ -566,6 +568,13 @@ def test_fast_path_statistics(torch_cuda):
             assert int(s["sse"][c]) == O.sse_int(frames[..., c], refd[..., c])
         assert s["nsamples"] == frames.size
         assert s["sumdiff"] == int((frames.astype(np.int64) - refd.astype(np.int64)).sum())
+        # float32 decoder: separate streaming pass over (original, decoded)
+        y32, s32 = _codec(block_size=8, q=q).decode(idx, (H, W), original=x, stats=True)
+        s32 = stats_dict(s32.cpu().numpy())
+        y32 = y32.cpu().numpy()
+        for c in range(3):
+            assert int(s32["sse"][c]) == O.sse_int(frames[..., c], y32[..., c])
+        assert s32["nsamples"] == frames.size
 
 
 def test_no_writes_outside_the_output_arrays(torch_cuda):

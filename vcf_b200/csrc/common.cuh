@@ -62,6 +62,7 @@ int launch_decode_fast(const DecArgs& a, int B, cudaStream_t s);
 // streaming statistics behind the fast path (kernels_stats.cu); VCFB_E_UNSUPP if unaligned
 int launch_index_stats(const uint8_t* idx, long long n_bytes, bool hist, unsigned long long* stats, cudaStream_t s);
 int launch_sse(const uint8_t* a, const uint8_t* b, long long n_bytes, unsigned long long* stats, cudaStream_t s);
+int launch_add_count(unsigned long long* stats, int slot, unsigned long long n, cudaStream_t s);
 
 // stand-alone colour codecs (kernels_color.cu)
 int launch_color_encode(const uint8_t* rgb, long long npx, double q, int color, uint16_t* out, cudaStream_t s);

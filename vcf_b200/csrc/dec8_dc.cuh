@@ -65,6 +65,68 @@ __device__ __forceinline__ void dc_blocks(const Lane& L, uint32_t w0, uint32_t w
 }
 
 
+// ---- distortion statistics fused into the float64 decoders (src/RDE.py:41-49) --------------
+// Each lane compares the 48 bytes it owns in a finished half-tile row (16 pixels of two blocks,
+// starting on a pixel boundary, so byte j of word k belongs to channel (4k + j) mod 3) with the
+// same bytes of the original frame: per-channel sum of squared differences through a masked
+// dp4a of the byte-wise absolute difference with itself, and the signed sum of differences.
+struct SseAcc {
+  unsigned ph[3];
+  int sx, sy, it;
+  unsigned long long tot[3];
+  long long sdiff;
+};
+__device__ __forceinline__ void sse_reset(SseAcc& A) {
+#pragma unroll
+  for (int p = 0; p < 3; ++p) { A.ph[p] = 0; A.tot[p] = 0; }
+  A.sx = A.sy = A.it = 0;
+  A.sdiff = 0;
+}
+__device__ __forceinline__ void sse_flush(SseAcc& A) {
+#pragma unroll
+  for (int p = 0; p < 3; ++p) { A.tot[p] += A.ph[p]; A.ph[p] = 0; }
+  A.sdiff += (long long)A.sx - A.sy;
+  A.sx = A.sy = A.it = 0;
+}
+__device__ __forceinline__ void sse_row48(SseAcc& A, const uint4 (&orig)[3], const unsigned char* mine) {
+  constexpr unsigned M[3][3] = {{0xFF0000FFu, 0x0000FF00u, 0x00FF0000u},
+                                {0x00FF0000u, 0xFF0000FFu, 0x0000FF00u},
+                                {0x0000FF00u, 0x00FF0000u, 0xFF0000FFu}};
+  const uint4* p = reinterpret_cast<const uint4*>(mine);
+  const uint4 y0 = p[0], y1 = p[1], y2 = p[2];
+  const unsigned xa[12] = {orig[0].x, orig[0].y, orig[0].z, orig[0].w, orig[1].x, orig[1].y,
+                           orig[1].z, orig[1].w, orig[2].x, orig[2].y, orig[2].z, orig[2].w};
+  const unsigned ya[12] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y, y1.z, y1.w, y2.x, y2.y, y2.z, y2.w};
+#pragma unroll
+  for (int k = 0; k < 12; ++k) {
+    const unsigned d = __vabsdiffu4(xa[k], ya[k]);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const unsigned dm = d & M[(4 * k) % 3][c];
+      A.ph[c] = __dp4a(dm, dm, A.ph[c]);
+    }
+    A.sx = __dp4a(xa[k], 0x01010101u, unsigned(A.sx));
+    A.sy = __dp4a(ya[k], 0x01010101u, unsigned(A.sy));
+  }
+  if (++A.it == 1024) sse_flush(A);        // 1024 * 48 * 65025 < 2^32
+}
+// end of the kernel: one set of atomics per warp
+__device__ __forceinline__ void sse_finish(SseAcc& A, unsigned long long* stats, int lane) {
+  sse_flush(A);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int p = 0; p < 3; ++p) A.tot[p] += __shfl_xor_sync(0xffffffffu, A.tot[p], o);
+    A.sdiff += __shfl_xor_sync(0xffffffffu, A.sdiff, o);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+      if (A.tot[p]) atomicAdd(stats + VCFB_STAT_SSE_R + p, A.tot[p]);
+    if (A.sdiff) atomicAdd(stats + VCFB_STAT_SUMDIFF, (unsigned long long)A.sdiff);
+  }
+}
+
 // ac24 of one half-tile: bits 6*pair + 3*block + {0,1,2} all set when the block carries any AC
 // index.  nz0, nz1: OR over the coefficient rows of (word ^ 0x80808080) of the lane's two words,
 // with the DC position (lane i1 == 0, row 0) masked out.

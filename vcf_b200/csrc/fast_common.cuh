@@ -45,6 +45,7 @@ struct FastArgs {
   int ntiles, tiles_x, ny, top;
   float q;
   float qtab[8][3];   // [u][c]: sgn_u * 2^(exp_u + colour exp_c + min_i exp_i) (/ q when q is 2^k)
+  unsigned long long* stats;   // packed encoder: accumulates NONZERO and SUMABS when set
 };
 
 struct FastDecArgs {
@@ -54,6 +55,11 @@ struct FastDecArgs {
   // `choice` is set, the kernel runs only if *choice == kind and exits at once otherwise.
   const int* choice;
   int kind;
+  // distortion statistics fused into the float64 decoders (kernels instantiated with SSE = true)
+  const uint8_t* original;
+  unsigned long long* stats;
+  long long frame_bytes;       // H * W * 3
+  int row_bytes;               // W * 3
 };
 enum { DEC_EXACT = 0, DEC_EXACT_DCSKIP = 1, DEC_TWO_TIER = 2 };
 __device__ __forceinline__ bool not_chosen(const FastDecArgs& a) {

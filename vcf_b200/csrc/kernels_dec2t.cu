@@ -197,7 +197,7 @@ __device__ __forceinline__ void exact_half(const HalfWords& hw, double* F, unsig
   else exact_half_call(hw, F, tb, h, i1, G1, G2, y2, sh0, q);
 }
 
-template <int NWARPS, int CTAS, int NST, bool UNROLL_C, bool INL, bool T1>
+template <int NWARPS, int CTAS, int NST, bool UNROLL_C, bool INL, bool T1, bool SSE>
 __global__ void __launch_bounds__(NWARPS * 32, CTAS)
 dec8_2t_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
                const FastDecArgs a) {
@@ -265,6 +265,18 @@ dec8_2t_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
   constexpr int MIXB[3] = {-128, -256, 128};
   // bytes of a lane's 6-byte run that belong to an AC index (lane i1 == 0, row u == 0 holds the DC)
   const uint32_t dcm = L.i1 == 0 ? 0u : 0xffffffffu;
+  SseAcc acc;
+  sse_reset(acc);
+  // the 48 bytes of the original frame under this lane's bytes of half h of a tile
+  auto load_orig = [&](int t, int h, uint4 (&o)[3]) {
+    int f, by, tx;
+    w.coords(t, f, by, tx);
+    const uint4* p = reinterpret_cast<const uint4*>(a.original + f * a.frame_bytes + (long long)(by * 8 + L.y2) * a.row_bytes +
+                                                    tx * (WT * 3) + 192 * h + 48 * L.G2);
+    o[0] = __ldg(p);
+    o[1] = __ldg(p + 1);
+    o[2] = __ldg(p + 2);
+  };
 
   int k = 0;
   for (int tile = w.tile; tile < w.ntiles; tile += w.stride, ++k) {
@@ -296,15 +308,20 @@ dec8_2t_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
 
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
+      uint4 og[3];
+      if (SSE) load_orig(tile, h, og);
+      const unsigned char* mine = tb + L.y2 * (WT * 3) + 192 * h + 48 * L.G2;
       const unsigned ac24 = half_ac24(L, nz[h][0], nz[h][1]);
       if (ac24 == 0u) {                              // DC-only half-tile: tier 2a for all 8 blocks
         dc_blocks(L, wd[h].w[0][0], wd[h].w[0][1], tb, h, 0xffu);
         __syncwarp();
+        if (SSE) sse_row48(acc, og, mine);
         continue;
       }
       if (!T1) {                                     // development variant: no tier 1 at all
         exact_half<INL>(wd[h], F, tb, h, L.i1, L.G1, L.G2, L.y2, L.sh0, L.q);
         __syncwarp();
+        if (SSE) sse_row48(acc, og, mine);
         continue;
       }
 
@@ -383,6 +400,7 @@ dec8_2t_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
         }
         __syncwarp();
       }
+      if (SSE) sse_row48(acc, og, mine);
     }
     tma::fence_proxy_async();
     __syncwarp();
@@ -398,14 +416,15 @@ dec8_2t_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
     __syncwarp();
   }
   if (lane == 0) tma::wait_group<0>();
+  if (SSE) sse_finish(acc, a.stats, lane);
 }
 
-template <int NWARPS, int CTAS, int NST, bool UNROLL_C, bool INL = false, bool T1 = true>
+template <int NWARPS, int CTAS, int NST, bool UNROLL_C, bool INL = false, bool T1 = true, bool SSE = false>
 int launch_t(const CUtensorMap& in_map, const CUtensorMap& out_map, const FastDecArgs& fa, cudaStream_t s) {
   int grid = sm_count() * CTAS;
   const int need = (fa.ntiles + NWARPS - 1) / NWARPS;
   if (grid > need) grid = need;
-  auto kern = dec8_2t_kernel<NWARPS, CTAS, NST, UNROLL_C, INL, T1>;
+  auto kern = dec8_2t_kernel<NWARPS, CTAS, NST, UNROLL_C, INL, T1, SSE>;
   const int smem_bytes = NWARPS * warp_smem(NST);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dec8_2t)");
@@ -420,6 +439,7 @@ int launch_t(const CUtensorMap& in_map, const CUtensorMap& out_map, const FastDe
 
 int launch_decode_2t(int cfg, const CUtensorMap& in_map, const CUtensorMap& out_map, const fast::FastDecArgs& fa,
                      cudaStream_t s) {
+  if (fa.stats) return launch_t<8, 1, 3, true, false, true, true>(in_map, out_map, fa, s);   // fused distortion statistics
   switch (cfg) {
     case 42: return launch_t<4, 2, 3, true>(in_map, out_map, fa, s);
     case 43: return launch_t<4, 3, 2, true>(in_map, out_map, fa, s);     // 12 warps per SM, 2-stage ring

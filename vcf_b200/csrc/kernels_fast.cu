@@ -447,7 +447,7 @@ constexpr int H64_F_BYTES = 3 * 8 * H64_PP * 8;
 constexpr int H64_WARP_SMEM = 26240;
 static_assert(NSTAGE * TILE + H64_F_BYTES + 8 * NSTAGE <= H64_WARP_SMEM, "decode f64 half-tile smem");
 
-template <bool EXACT, int NWARPS, int CTAS, bool DCSKIP>
+template <bool EXACT, int NWARPS, int CTAS, bool DCSKIP, bool SSE>
 __global__ void __launch_bounds__(NWARPS * 32, CTAS)
 dec8_f64h_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
                  const FastDecArgs a) {
@@ -506,6 +506,18 @@ dec8_f64h_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_consta
   Lane L;
   L.i1 = i1; L.G1 = G1; L.G2 = G2; L.y2 = y2; L.sh0 = sh0; L.q = q;
   const uint32_t dcm = i1 == 0 ? 0u : 0xffffffffu;     // row 0 of column 0 holds the DC indices
+  SseAcc acc;
+  sse_reset(acc);
+  // the 48 bytes of the original frame under this lane's bytes of half h of a tile
+  auto load_orig = [&](int t, int h, uint4 (&o)[3]) {
+    int f, by, tx;
+    w.coords(t, f, by, tx);
+    const uint4* p = reinterpret_cast<const uint4*>(a.original + f * a.frame_bytes + (long long)(by * 8 + y2) * a.row_bytes +
+                                                    tx * (WT * 3) + 192 * h + 48 * G2);
+    o[0] = __ldg(p);
+    o[1] = __ldg(p + 1);
+    o[2] = __ldg(p + 2);
+  };
 
   int k = 0;
   for (int tile = w.tile; tile < w.ntiles; tile += w.stride, ++k) {
@@ -542,12 +554,23 @@ dec8_f64h_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_consta
       dc_tile = !__any_sync(0xffffffffu, (lo | hi) != 0u);
     }
     if (dc_tile) {
+      uint4 og[2][3];
+      if (SSE) {
+        load_orig(tile, 0, og[0]);
+        load_orig(tile, 1, og[1]);
+      }
       dc_blocks(L, wd[0][0][0], wd[0][0][1], tb, 0, 0xffu);
       dc_blocks(L, wd[1][0][0], wd[1][0][1], tb, 1, 0xffu);
       __syncwarp();
+      if (SSE) {
+        sse_row48(acc, og[0], tb + y2 * (WT * 3) + 48 * G2);
+        sse_row48(acc, og[1], tb + y2 * (WT * 3) + 192 + 48 * G2);
+      }
     } else {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
+      uint4 og[3];
+      if (SSE) load_orig(tile, h, og);
       // ---- pass 1: dequantise + inverse DCT over u, 2 blocks per lane and channel ------
       {
         T* fw = F + i1 * H64_P + 2 * G1;
@@ -608,6 +631,7 @@ dec8_f64h_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_consta
         orow[0] = make_uint4(ww[0], ww[1], ww[2], ww[3]);
         orow[1] = make_uint4(ww[4], ww[5], ww[6], ww[7]);
         orow[2] = make_uint4(ww[8], ww[9], ww[10], ww[11]);
+        if (SSE) sse_row48(acc, og, reinterpret_cast<const unsigned char*>(orow));   // the lane's own bytes
       }
       __syncwarp();
     }
@@ -626,6 +650,7 @@ dec8_f64h_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_consta
     __syncwarp();
   }
   if (lane == 0) tma::wait_group<0>();
+  if (SSE) sse_finish(acc, a.stats, lane);
 }
 
 // ---- host side -----------------------------------------------------------------
@@ -695,7 +720,12 @@ int launch_encode_fast(const EncArgs& a, int B, cudaStream_t s) {
   if (a.flags & (VCFB_F_NO_SUBBANDS | VCFB_F_PERCEPTUAL | VCFB_F_FP64)) return VCFB_E_UNSUPP;
   const Geom& g = a.g;
   if (!fast_geometry_ok(g, a.rgb, a.idx)) return VCFB_E_UNSUPP;
-  if (a.stats) {   // statistics are a separate streaming pass over the indices (kernels_stats.cu)
+  const bool exact = !(a.flags & VCFB_F_CONTRACT);
+  static const bool scalar_enc = getenv("VCFB_ENC_SCALAR") != nullptr;
+  // the packed exact encoder counts non-zero indices and sum |k| itself; the histogram, the
+  // scalar / contracted variants take a separate streaming pass over the indices (kernels_stats.cu)
+  const bool fused_stats = a.stats && exact && !scalar_enc && !(a.flags & VCFB_F_HIST);
+  if (a.stats && !fused_stats) {
     EncArgs b = a;
     b.stats = nullptr;
     int rc = launch_encode_fast(b, B, s);
@@ -722,7 +752,11 @@ int launch_encode_fast(const EncArgs& a, int B, cudaStream_t s) {
       fa.qtab[u][c] = float(sc);                             // a power of two: exact
     }
 
-  const bool exact = !(a.flags & VCFB_F_CONTRACT);
+  fa.stats = fused_stats ? a.stats : nullptr;
+  if (fused_stats) {
+    int rc = launch_add_count(a.stats, VCFB_STAT_NINDICES, (unsigned long long)a.n_frames * g.Hp * g.Wp * 3, s);
+    if (rc) return rc;
+  }
   // development knob VCFB_ENC_CFG: 5x2 reproduces the scheduler imbalance of 5 warps per CTA,
   // 4x3 the 2-stage ring with 12 warps per SM (both measured slower)
   switch (dev_cfg("VCFB_ENC_CFG")) {
@@ -749,13 +783,13 @@ static int launch_dec_t(const CUtensorMap& in_map, const CUtensorMap& out_map, c
   return VCFB_OK;
 }
 
-template <int NWARPS, int CTAS, bool DCSKIP = true>
+template <int NWARPS, int CTAS, bool DCSKIP = true, bool SSE = false>
 static int launch_dec_f64h(const CUtensorMap& in_map, const CUtensorMap& out_map, const FastDecArgs& fa,
                            cudaStream_t s) {
   int grid = sm_count() * CTAS;
   const int need = (fa.ntiles + NWARPS - 1) / NWARPS;
   if (grid > need) grid = need;
-  auto kern = dec8_f64h_kernel<true, NWARPS, CTAS, DCSKIP>;
+  auto kern = dec8_f64h_kernel<true, NWARPS, CTAS, DCSKIP, SSE>;
   const int smem_bytes = NWARPS * H64_WARP_SMEM;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dec8_f64h)");
@@ -887,7 +921,7 @@ static ProbeSlot* probe_slot() {
 static int launch_decode_f64_probed(const DecArgs& a, const CUtensorMap& in_map, const CUtensorMap& out_map, FastDecArgs fa,
                              cudaStream_t s) {
   ProbeSlot* slot = fa.ntiles >= PROBE_MIN_TILES ? probe_slot() : nullptr;
-  if (!slot) return launch_dec_f64h<8, 1, false>(in_map, out_map, fa, s);
+  if (!slot) return fa.stats ? launch_dec_f64h<8, 1, false, true>(in_map, out_map, fa, s) : launch_dec_f64h<8, 1, false>(in_map, out_map, fa, s);
   const Geom& g = a.g;
   ProbeArgs pa;
   pa.idx = a.idx;
@@ -905,10 +939,10 @@ static int launch_decode_f64_probed(const DecArgs& a, const CUtensorMap& in_map,
   note_extra_launches(1);
   fa.choice = &slot->choice;
   fa.kind = DEC_EXACT;
-  int rc = launch_dec_f64h<8, 1, false>(in_map, out_map, fa, s);
+  int rc = fa.stats ? launch_dec_f64h<8, 1, false, true>(in_map, out_map, fa, s) : launch_dec_f64h<8, 1, false>(in_map, out_map, fa, s);
   if (rc) return rc;
   fa.kind = DEC_EXACT_DCSKIP;
-  rc = launch_dec_f64h<8, 1, true>(in_map, out_map, fa, s);
+  rc = fa.stats ? launch_dec_f64h<8, 1, true, true>(in_map, out_map, fa, s) : launch_dec_f64h<8, 1, true>(in_map, out_map, fa, s);
   if (rc) return rc;
   fa.kind = DEC_TWO_TIER;
   return launch_decode_2t(0, in_map, out_map, fa, s);
@@ -921,7 +955,9 @@ int launch_decode_fast(const DecArgs& a, int B, cudaStream_t s) {
   if ((a.stats != nullptr) != (a.original != nullptr)) return VCFB_E_UNSUPP;
   if (a.q_int < 1 || a.q_int > 255) return VCFB_E_UNSUPP;
   const Geom& g = a.g;
-  if (a.stats) {   // distortion = a separate streaming pass over (original, decoded)
+  const bool fused_sse = a.stats && (a.flags & VCFB_F_FP64) && dev_cfg("VCFB_DEC_CFG") == 0 &&
+                         !(reinterpret_cast<uintptr_t>(a.original) & 15);
+  if (a.stats && !fused_sse) {   // distortion = a separate streaming pass over (original, decoded)
     if (reinterpret_cast<uintptr_t>(a.original) & 15) return VCFB_E_UNSUPP;
     DecArgs b = a;
     b.stats = nullptr;
@@ -946,6 +982,16 @@ int launch_decode_fast(const DecArgs& a, int B, cudaStream_t s) {
   fa.q = a.q_int;
   fa.choice = nullptr;
   fa.kind = 0;
+  fa.original = nullptr;
+  fa.stats = nullptr;
+  fa.frame_bytes = (long long)g.H * g.W * 3;
+  fa.row_bytes = g.W * 3;
+  if (fused_sse) {     // the float64 decoders accumulate SSE / SUMDIFF themselves; the sample count is known here
+    fa.original = a.original;
+    fa.stats = a.stats;
+    int rc = launch_add_count(a.stats, VCFB_STAT_NSAMPLES, (unsigned long long)a.n_frames * g.H * g.W * 3, s);
+    if (rc) return rc;
+  }
   if (a.flags & VCFB_F_FP64) {
     // default: probe + device-side choice between the three float64 decoders.  Development knob
     // VCFB_DEC_CFG forces one: 9x2 exact chain, 9x1 exact chain + DC-only shortcut, 8x1 (and the

@@ -27,7 +27,7 @@ __device__ __forceinline__ float2 dotf2(unsigned pa, unsigned pb, int coef, int 
   return Ops<float2, true>::add(r, make_float2(-MAGIC_F, -MAGIC_F));
 }
 
-template <bool QPOW2, int NWARPS, int CTAS, int NST>
+template <bool QPOW2, int NWARPS, int CTAS, int NST, bool STATS>
 __global__ void __launch_bounds__(NWARPS * 32, CTAS)
 enc8p_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
                   const FastArgs a) {
@@ -86,6 +86,7 @@ enc8p_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
     qs[c][1] = a.qtab[u][c] * 2.0f;
   }
   const float qf = a.q;
+  unsigned st_nz = 0, st_abs = 0;      // STATS: non-zero indices and sum |k| of this lane (src/IPP_DCT.py:273-292)
 
   int k = 0;
   for (int tile = w.tile; tile < w.ntiles; tile += w.stride, ++k) {
@@ -168,9 +169,22 @@ enc8p_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
             kk[2 * pp + 1][c] = __float2int_rz(ty);
           }
         uint32_t* o = ow + i * 96;
-        o[0] = pack4(kk[0][0], kk[0][1], kk[0][2], kk[1][0]) ^ 0x80808080u;
-        o[1] = pack4(kk[1][1], kk[1][2], kk[2][0], kk[2][1]) ^ 0x80808080u;
-        o[2] = pack4(kk[2][2], kk[3][0], kk[3][1], kk[3][2]) ^ 0x80808080u;
+        const uint32_t w0 = pack4(kk[0][0], kk[0][1], kk[0][2], kk[1][0]) ^ 0x80808080u;
+        const uint32_t w1 = pack4(kk[1][1], kk[1][2], kk[2][0], kk[2][1]) ^ 0x80808080u;
+        const uint32_t w2 = pack4(kk[2][2], kk[3][0], kk[3][1], kk[3][2]) ^ 0x80808080u;
+        o[0] = w0;
+        o[1] = w1;
+        o[2] = w2;
+        if (STATS) {
+          // |k| per byte = |byte - 128| (wrapped indices count as the byte they became, like the
+          // streaming pass over the stored array does)
+          const uint32_t d0 = __vabsdiffu4(w0, 0x80808080u), d1 = __vabsdiffu4(w1, 0x80808080u),
+                         d2 = __vabsdiffu4(w2, 0x80808080u);
+          st_abs = __dp4a(d0, 0x01010101u, __dp4a(d1, 0x01010101u, __dp4a(d2, 0x01010101u, st_abs)));
+          st_nz += __popc((d0 | ((d0 & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u) +
+                   __popc((d1 | ((d1 & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u) +
+                   __popc((d2 | ((d2 & 0x7f7f7f7fu) + 0x7f7f7f7fu)) & 0x80808080u);
+        }
       }
     }
     tma::fence_proxy_async();
@@ -187,6 +201,17 @@ enc8p_fast_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_const
     __syncwarp();
   }
   if (lane == 0) tma::wait_group<0>();
+  if (STATS) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      st_nz += __shfl_xor_sync(0xffffffffu, st_nz, o);
+      st_abs += __shfl_xor_sync(0xffffffffu, st_abs, o);
+    }
+    if (lane == 0) {
+      atomicAdd(a.stats + VCFB_STAT_NONZERO, (unsigned long long)st_nz);
+      atomicAdd(a.stats + VCFB_STAT_SUMABS, (unsigned long long)st_abs);
+    }
+  }
 }
 
 
@@ -196,7 +221,8 @@ int launch_t(bool qpow2, const CUtensorMap& in_map, const CUtensorMap& out_map, 
   const int need = (fa.ntiles + NWARPS - 1) / NWARPS;
   if (grid > need) grid = need;
   void (*kern)(const CUtensorMap, const CUtensorMap, const FastArgs) =
-      qpow2 ? enc8p_fast_kernel<true, NWARPS, CTAS, NST> : enc8p_fast_kernel<false, NWARPS, CTAS, NST>;
+      fa.stats ? (qpow2 ? enc8p_fast_kernel<true, NWARPS, CTAS, NST, true> : enc8p_fast_kernel<false, NWARPS, CTAS, NST, true>)
+               : (qpow2 ? enc8p_fast_kernel<true, NWARPS, CTAS, NST, false> : enc8p_fast_kernel<false, NWARPS, CTAS, NST, false>);
   const int smem_bytes = NWARPS * enc_warp_smem(NST);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(enc8p_fast)");

@@ -136,6 +136,14 @@ __global__ void add_counts_kernel(unsigned long long* stats, int slot, unsigned 
 
 }  // namespace
 
+int launch_add_count(unsigned long long* stats, int slot, unsigned long long n, cudaStream_t s) {
+  add_counts_kernel<<<1, 1, 0, s>>>(stats, slot, n);
+  note_extra_launches(1);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "add_counts_kernel launch");
+  return VCFB_OK;
+}
+
 // idx: n_bytes uint8 indices, 16-byte aligned, n_bytes % 16 == 0 (true for whole fast-path frames)
 int launch_index_stats(const uint8_t* idx, long long n_bytes, bool hist, unsigned long long* stats, cudaStream_t s) {
   if ((reinterpret_cast<uintptr_t>(idx) & 15) || (n_bytes & 15)) return VCFB_E_UNSUPP;
