@@ -537,22 +537,28 @@ dec8_f64h_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_consta
         }
     }
     __syncwarp();
-    // A tile without any AC index (smooth content at a coarse step): two multiplications per
-    // block and channel instead of the transform (dec8_dc.cuh).
-    bool dc_tile = false;
+    // Which channels carry AC indices, per half-tile (bit 3h + c).  A channel without any is not
+    // transformed: every sample of block b equals (q k_b c0) c0 exactly (dec8_dc.cuh) -- smooth
+    // content at a coarse step, and the chroma planes of most natural content from q ~ 24 up.
+    unsigned chan6 = 0x3fu;
     if (DCSKIP) {
-      uint32_t nz0 = ((wd[0][0][0] ^ 0x80808080u) | (wd[1][0][0] ^ 0x80808080u)) & dcm;
-      uint32_t nz1 = ((wd[0][0][1] ^ 0x80808080u) | (wd[1][0][1] ^ 0x80808080u)) & dcm;
+      unsigned f6 = 0;
 #pragma unroll
-      for (int h = 0; h < 2; ++h)
+      for (int h = 0; h < 2; ++h) {
+        uint32_t nz0 = (wd[h][0][0] ^ 0x80808080u) & dcm, nz1 = (wd[h][0][1] ^ 0x80808080u) & dcm;
 #pragma unroll
         for (int uu = 1; uu < 8; ++uu) {
           nz0 |= wd[h][uu][0] ^ 0x80808080u;
           nz1 |= wd[h][uu][1] ^ 0x80808080u;
         }
-      const uint32_t lo = __funnelshift_r(nz0, nz1, sh0), hi = (nz1 >> sh0) & 0xffffu;
-      dc_tile = !__any_sync(0xffffffffu, (lo | hi) != 0u);
+        // the lane's 6-byte run: Y Co Cg Y | Co Cg
+        const uint32_t lo = __funnelshift_r(nz0, nz1, sh0), hi = nz1 >> sh0;
+        f6 |= (((lo & 0xff0000ffu) ? 1u : 0u) | (((lo & 0x0000ff00u) | (hi & 0x000000ffu)) ? 2u : 0u) |
+               (((lo & 0x00ff0000u) | (hi & 0x0000ff00u)) ? 4u : 0u)) << (3 * h);
+      }
+      chan6 = __reduce_or_sync(0xffffffffu, f6);
     }
+    const bool dc_tile = DCSKIP && chan6 == 0u;
     if (dc_tile) {
       uint4 og[2][3];
       if (SSE) {
@@ -576,6 +582,7 @@ dec8_f64h_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_consta
         T* fw = F + i1 * H64_P + 2 * G1;
 #pragma unroll 1
         for (int c = 0; c < 3; ++c) {
+          if (DCSKIP && !((chan6 >> (3 * h + c)) & 1u)) continue;      // no AC index in this channel
           T v[2][8];
 #pragma unroll
           for (int uu = 0; uu < 8; ++uu) {
@@ -597,18 +604,32 @@ dec8_f64h_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_consta
       {
         const T* fr = F + y2 * H64_PP + 2 * G2;
         T v[3][2][8];
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const double2 t2 = *reinterpret_cast<const double2*>(fr + c * 8 * H64_PP + i * H64_P);
-            v[c][0][i] = t2.x;
-            v[c][1][i] = t2.y;
-          }
+        const unsigned chan3 = (chan6 >> (3 * h)) & 7u;
+        uint32_t yccA = 0, yccB = 0;            // DC index bytes (Y, Co, Cg) of the lane's two blocks
+        if (DCSKIP && chan3 != 7u) {
+          const uint32_t lo = __funnelshift_r(wd[h][0][0], wd[h][0][1], sh0), hi = wd[h][0][1] >> sh0;
+          yccA = __shfl_sync(0xffffffffu, lo, 8 * G2);                          // lane (i1 = 0, pair G2) holds them
+          yccB = __shfl_sync(0xffffffffu, __byte_perm(lo, hi, 0x0543), 8 * G2);
+        }
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-          dct8_inv<T, EXACT>(v[c][0]);
-          dct8_inv<T, EXACT>(v[c][1]);
+          if (!DCSKIP || ((chan3 >> c) & 1u)) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const double2 t2 = *reinterpret_cast<const double2*>(fr + c * 8 * H64_PP + i * H64_P);
+              v[c][0][i] = t2.x;
+              v[c][1][i] = t2.y;
+            }
+            dct8_inv<T, EXACT>(v[c][0]);
+            dct8_inv<T, EXACT>(v[c][1]);
+          } else {
+            const T ka = dc_chain(int((yccA >> (8 * c)) & 255u), q), kb = dc_chain(int((yccB >> (8 * c)) & 255u), q);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              v[c][0][i] = ka;
+              v[c][1][i] = kb;
+            }
+          }
         }
         int px[2][8][3];
 #pragma unroll
@@ -804,19 +825,22 @@ static int launch_dec_f64h(const CUtensorMap& in_map, const CUtensorMap& out_map
 // ---- probe: which float64 decoder suits this batch ------------------------------------------
 // All three decoders give identical bytes; they differ in speed by content:
 //   * exact chain (dec8_f64h_kernel): the reference's operation sequence for every sample;
-//   * the same with the DC-only tile shortcut: pays ~4 % on tiles that have AC indices, wins
-//     3.7x on tiles that have none (smooth content at a coarse step);
+//   * the same with the DC-only shortcut per (half-tile, channel): pays ~4 % where every channel
+//     has AC indices, skips the transform of a channel that has none (the chroma planes of most
+//     natural content from q ~ 24 up) and runs at HBM speed on tiles without any (smooth content
+//     at a coarse step);
 //   * two-tier (kernels_dec2t.cu): 27 % faster when exact-integer samples are rare, i.e. when
 //     the indices are dense; up to 1.8x slower when they are sparse (+-1 indices that cancel).
-// One CTA reads 256 tiles spread over the batch, counts DC-only tiles and non-zero AC indices,
-// and writes its choice to a slot in device memory; the three kernels are launched behind it and
-// the two that were not chosen return at once.  Correctness never depends on the choice.
+// 32 CTAs read 256 tiles spread over the batch and count sparse blocks and (tile, channel) pairs
+// without AC indices; the last one writes the choice to a slot in device memory.  The three
+// kernels are launched behind it and the two that were not chosen return at once.  Correctness
+// never depends on the choice.
 constexpr int PROBE_TILES = 256;
 constexpr int PROBE_CTAS = 32;             // x 8 warps x 1 tile
 constexpr int PROBE_MIN_TILES = 4096;      // smaller jobs: not worth three extra launches
 
 struct ProbeSlot {
-  int sparse, dc_tiles, ticket, choice;    // the first three are zero between launches
+  int sparse, dc_chan, ticket, choice;     // the first three are zero between launches
 };
 
 struct ProbeArgs {
@@ -835,11 +859,14 @@ __device__ __forceinline__ uint32_t nonzero_flags(uint32_t x) {      // 0x80 in 
 // Counts, per sampled tile, the non-zero AC indices of each of its 16 blocks (all channels).
 // A block with 1..6 of them is "sparse": the kind whose samples land on exact integers.
 __global__ void __launch_bounds__(256, 1) dec8_probe_kernel(const ProbeArgs a) {
-  __shared__ int s_sparse, s_dc;
+  __shared__ int s_sparse, s_dc;            // sparse blocks; (tile, channel) pairs without AC indices
   if (threadIdx.x == 0) {
     s_sparse = 0;
     s_dc = 0;
   }
+  constexpr unsigned CH[3][3] = {{0xFF0000FFu, 0x0000FF00u, 0x00FF0000u},     // bytes of channel c in word k,
+                                 {0x00FF0000u, 0xFF0000FFu, 0x0000FF00u},     // k mod 3 = 0, 1, 2
+                                 {0x0000FF00u, 0x00FF0000u, 0xFF0000FFu}};
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int step = a.ntiles / PROBE_TILES;
@@ -849,6 +876,7 @@ __global__ void __launch_bounds__(256, 1) dec8_probe_kernel(const ProbeArgs a) {
     const int f = t / a.per_frame, rem = t - f * a.per_frame;
     const int by = rem / a.tiles_x, tx = rem - by * a.tiles_x;
     uint32_t acc[4] = {0u, 0u, 0u, 0u};        // 16 byte-wide counters: block b in byte b & 3 of acc[b >> 2]
+    uint32_t chf[3] = {0u, 0u, 0u};            // non-zero flags per channel
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       const int seg = lane + 32 * r, j = seg >> 3, i = seg & 7;          // subband (j, i): 16 blocks x 3 bytes
@@ -865,6 +893,8 @@ __global__ void __launch_bounds__(256, 1) dec8_probe_kernel(const ProbeArgs a) {
           const uint32_t c2 = __popc(f1 & 0x80800000u) + __popc(f2 & 0x00000080u);
           const uint32_t c3 = __popc(f2 & 0x80808000u);
           acc[g] += c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);          // <= 3 per segment, 189 per tile: no carry
+#pragma unroll
+          for (int c = 0; c < 3; ++c) chf[c] |= (f0 & CH[0][c]) | (f1 & CH[1][c]) | (f2 & CH[2][c]);
         }
       }
     }
@@ -872,7 +902,8 @@ __global__ void __launch_bounds__(256, 1) dec8_probe_kernel(const ProbeArgs a) {
     for (int g = 0; g < 4; ++g) acc[g] = __reduce_add_sync(0xffffffffu, acc[g]);
     const uint32_t mine = lane < 16 ? (acc[lane >> 2] >> (8 * (lane & 3))) & 0xffu : 0xffu;
     nsparse += __popc(__ballot_sync(0xffffffffu, mine >= 1u && mine <= 6u));
-    ndc += (acc[0] | acc[1] | acc[2] | acc[3]) == 0u;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) ndc += !__any_sync(0xffffffffu, chf[c] != 0u);
   }
   if (lane == 0) {
     atomicAdd(&s_sparse, nsparse);
@@ -882,14 +913,14 @@ __global__ void __launch_bounds__(256, 1) dec8_probe_kernel(const ProbeArgs a) {
   if (threadIdx.x == 0) {
     ProbeSlot* sl = a.slot;
     atomicAdd(&sl->sparse, s_sparse);
-    atomicAdd(&sl->dc_tiles, s_dc);
+    atomicAdd(&sl->dc_chan, s_dc);
     __threadfence();
     if (atomicAdd(&sl->ticket, 1) == PROBE_CTAS - 1) {      // last CTA: decide, and leave the slot clean
       __threadfence();
-      const int sparse = atomicExch(&sl->sparse, 0), dc = atomicExch(&sl->dc_tiles, 0);
+      const int sparse = atomicExch(&sl->sparse, 0), dc = atomicExch(&sl->dc_chan, 0);
       int kind = DEC_EXACT;
       if (50 * sparse <= PROBE_TILES * 16) kind = DEC_TWO_TIER;         // <= 2 % sparse blocks
-      else if (16 * dc > PROBE_TILES) kind = DEC_EXACT_DCSKIP;          // > 1/16 of the tiles DC-only
+      else if (8 * dc > 3 * PROBE_TILES) kind = DEC_EXACT_DCSKIP;       // > 1/8 of the (tile, channel) pairs without AC
       sl->choice = kind;
       sl->ticket = 0;
     }

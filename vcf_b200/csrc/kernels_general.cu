@@ -207,22 +207,21 @@ __global__ void __launch_bounds__(NT) encode_kernel(const EncArgs a) {
       }
     }
   } else {
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
+    // work items = (channel, pixel column): all NT threads stay busy when TW < NT
+    for (int wi = tid; wi < 3 * TW; wi += NT) {
+      const int c = wi / TW, x = wi - c * TW;
       const T cs = T(a.color == VCFB_COLOR_YCOCG ? (c == 1 ? 0.5 : 0.25) : 1.0);
-      for (int x = tid; x < TW; x += NT) {
-        T v[B];
+      T v[B];
 #pragma unroll
-        for (int r = 0; r < B; ++r) {
-          const uint8_t* px = raw + r * RAWP + x * 3;
-          v[r] = color_fwd<T, EXACT>(a.color, c, px[0], px[1], px[2]);
-        }
-        D::template run<T, EXACT>(v);
-        const int xs = L::swz(x);
-#pragma unroll
-        for (int u = 0; u < B; ++u)
-          F[(c * B + u) * FP + xs] = O::mul(v[u], T(M::sgn(u) * p2(M::exp(u))) * cs);       // exact factor
+      for (int r = 0; r < B; ++r) {
+        const uint8_t* px = raw + r * RAWP + x * 3;
+        v[r] = color_fwd<T, EXACT>(a.color, c, px[0], px[1], px[2]);
       }
+      D::template run<T, EXACT>(v);
+      const int xs = L::swz(x);
+#pragma unroll
+      for (int u = 0; u < B; ++u)
+        F[(c * B + u) * FP + xs] = O::mul(v[u], T(M::sgn(u) * p2(M::exp(u))) * cs);       // exact factor
     }
   }
   __syncthreads();
@@ -233,9 +232,9 @@ __global__ void __launch_bounds__(NT) encode_kernel(const EncArgs a) {
     const T q = T(a.q);
     const T inv_q = T(a.inv_q);
     const bool fastq = a.q_pow2 && !percep;
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      for (int t = tid; t < TW; t += NT) {
+    {
+      for (int wi = tid; wi < 3 * TW; wi += NT) {     // work items = (channel, block, row u)
+        const int c = wi / TW, t = wi - c * TW;
         const int bx = t % TBX, u = t / TBX;      // lanes = consecutive blocks: conflict-free staging stores
         if (bx >= nbx) continue;
         T v[B];
@@ -412,9 +411,9 @@ __global__ void __launch_bounds__(NT) decode_kernel(const DecArgs a) {
   __syncthreads();
 
   // ---- pass 1: dequantise, inverse DCT along axis 0 ---------------------------
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    for (int x = tid; x < TW; x += NT) {
+  {
+    for (int wi = tid; wi < 3 * TW; wi += NT) {       // work items = (channel, coefficient column)
+      const int c = wi / TW, x = wi - c * TW;
       const int bx = x / B, i = x % B;
       if (bx >= nbx) continue;
       T v[B];
@@ -450,9 +449,9 @@ __global__ void __launch_bounds__(NT) decode_kernel(const DecArgs a) {
   __syncthreads();
 
   // ---- pass 2: inverse DCT along axis 1 (in place in smem) --------------------
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    for (int t = tid; t < TW; t += NT) {
+  {
+    for (int wi = tid; wi < 3 * TW; wi += NT) {       // work items = (channel, block, pixel row)
+      const int c = wi / TW, t = wi - c * TW;
       const int r = t % B, bx = t / B;
       if (bx >= nbx) continue;
       T v[B];
