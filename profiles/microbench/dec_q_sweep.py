@@ -33,7 +33,7 @@ def timed(fn, reps=5):
     return e0.elapsed_time(e1) / reps
 
 
-cfgs = [("probed", None), ("2t", "8x1"), ("exact+dcskip", "9x1"), ("exact old", "9x2")]
+cfgs = [("probed", None), ("2t", "8x1"), ("exact+dcskip", "9x1"), ("exact", "9x2")]
 print(f"{n} frames {W}x{H}; ms per launch")
 for name, x in (("natural", nat), ("noise", noise)):
     for q in (4, 8, 12, 16, 24, 32, 64):
@@ -47,7 +47,7 @@ for name, x in (("natural", nat), ("noise", noise)):
             else:
                 os.environ.pop("VCFB_DEC_CFG", None)
             row.append(timed(lambda: dec.decode(idx, (H, W), out=y)))
-            outs.append(y.clone() if label in ("probed", "exact old") else None)
+            outs.append(y.clone() if label in ("probed", "exact") else None)
         same = bool(torch.equal(outs[0], outs[-1]))
         ref = outs[-1]
         dec32 = Codec(block_size=8, q=q)

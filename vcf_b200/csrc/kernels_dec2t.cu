@@ -28,8 +28,13 @@
 //         a half-tile that is DC-only throughout skips tier 1 altogether;
 //       * otherwise the half-tile of 8 blocks is recomputed with the exact codelets.
 //
-// Pipeline, tile shape, lane mapping and shared-memory layout are those of
-// dec8_f64h_kernel (kernels_fast.cu).
+// Pays off when exact-integer samples are rare (dense indices); sparse indices put them into
+// most half-tiles and tier 1 is then wasted work, so the probe of kernels_fast.cu decides per
+// batch whether this kernel or the single-tier exact one runs.  exact_half stays out of line:
+// inlined, the loop body no longer fits the instruction cache and the kernel runs 2-3x slower.
+//
+// Pipeline, tile shape and lane mapping are those of dec8_f64h_kernel (kernels_fast.cu); the
+// intermediate is XOR-swizzled instead of padded (12 KB per warp).
 #include "fast_common.cuh"
 #include "dec8_dc.cuh"
 
@@ -121,8 +126,7 @@ struct HalfWords {
   uint32_t w[8][2];      // [coefficient row u][word]: the lane's 6-byte run of one half-tile
 };
 
-template <bool INL>
-__device__ __forceinline__ void exact_half_body(const HalfWords& hw, double* F, unsigned char* tb, int h, int i1, int G1,
+__device__ __noinline__ void exact_half(const HalfWords hw, double* F, unsigned char* tb, int h, int i1, int G1,
                                         int G2, int y2, int sh0, int q) {
   using O = Ops<double, true>;
   constexpr double SCALE = p2(2 * M8I::exp(0));
@@ -186,18 +190,7 @@ __device__ __forceinline__ void exact_half_body(const HalfWords& hw, double* F, 
   }
 }
 
-__device__ __noinline__ void exact_half_call(const HalfWords hw, double* F, unsigned char* tb, int h, int i1, int G1,
-                                             int G2, int y2, int sh0, int q) {
-  exact_half_body<false>(hw, F, tb, h, i1, G1, G2, y2, sh0, q);
-}
-template <bool INL>
-__device__ __forceinline__ void exact_half(const HalfWords& hw, double* F, unsigned char* tb, int h, int i1, int G1,
-                                           int G2, int y2, int sh0, int q) {
-  if (INL) exact_half_body<true>(hw, F, tb, h, i1, G1, G2, y2, sh0, q);
-  else exact_half_call(hw, F, tb, h, i1, G1, G2, y2, sh0, q);
-}
-
-template <int NWARPS, int CTAS, int NST, bool UNROLL_C, bool INL, bool T1, bool SSE>
+template <int NWARPS, int CTAS, int NST, bool UNROLL_C, bool SSE>
 __global__ void __launch_bounds__(NWARPS * 32, CTAS)
 dec8_2t_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
                const FastDecArgs a) {
@@ -318,13 +311,6 @@ dec8_2t_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
         if (SSE) sse_row48(acc, og, mine);
         continue;
       }
-      if (!T1) {                                     // development variant: no tier 1 at all
-        exact_half<INL>(wd[h], F, tb, h, L.i1, L.G1, L.G2, L.y2, L.sh0, L.q);
-        __syncwarp();
-        if (SSE) sse_row48(acc, og, mine);
-        continue;
-      }
-
       // ---- tier 1, pass 1: index colour mix, int -> double, scaled inverse DCT over u ------
       {
         double* fw0 = F + f_store_off(L.i1, L.G1);
@@ -394,7 +380,7 @@ dec8_2t_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
 #pragma unroll
         for (int j = 0; j < 8; ++j) ac8 |= ((ac24 >> (3 * j)) & 1u) << j;
         if (tie8 & ac8) {
-          exact_half<INL>(wd[h], F, tb, h, L.i1, L.G1, L.G2, L.y2, L.sh0, L.q);
+          exact_half(wd[h], F, tb, h, L.i1, L.G1, L.G2, L.y2, L.sh0, L.q);
         } else {
           dc_blocks(L, wd[h].w[0][0], wd[h].w[0][1], tb, h, tie8);
         }
@@ -419,12 +405,12 @@ dec8_2t_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
   if (SSE) sse_finish(acc, a.stats, lane);
 }
 
-template <int NWARPS, int CTAS, int NST, bool UNROLL_C, bool INL = false, bool T1 = true, bool SSE = false>
+template <int NWARPS, int CTAS, int NST, bool UNROLL_C, bool SSE = false>
 int launch_t(const CUtensorMap& in_map, const CUtensorMap& out_map, const FastDecArgs& fa, cudaStream_t s) {
   int grid = sm_count() * CTAS;
   const int need = (fa.ntiles + NWARPS - 1) / NWARPS;
   if (grid > need) grid = need;
-  auto kern = dec8_2t_kernel<NWARPS, CTAS, NST, UNROLL_C, INL, T1, SSE>;
+  auto kern = dec8_2t_kernel<NWARPS, CTAS, NST, UNROLL_C, SSE>;
   const int smem_bytes = NWARPS * warp_smem(NST);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(dec8_2t)");
@@ -439,13 +425,10 @@ int launch_t(const CUtensorMap& in_map, const CUtensorMap& out_map, const FastDe
 
 int launch_decode_2t(int cfg, const CUtensorMap& in_map, const CUtensorMap& out_map, const fast::FastDecArgs& fa,
                      cudaStream_t s) {
-  if (fa.stats) return launch_t<8, 1, 3, true, false, true, true>(in_map, out_map, fa, s);   // fused distortion statistics
+  if (fa.stats) return launch_t<8, 1, 3, true, true>(in_map, out_map, fa, s);   // fused distortion statistics
   switch (cfg) {
     case 42: return launch_t<4, 2, 3, true>(in_map, out_map, fa, s);
     case 43: return launch_t<4, 3, 2, true>(in_map, out_map, fa, s);     // 12 warps per SM, 2-stage ring
-    case 81: return launch_t<8, 1, 3, true, true>(in_map, out_map, fa, s);    // exact chain inlined
-    case 71: return launch_t<8, 1, 3, true, true, false>(in_map, out_map, fa, s);   // no tier 1, inlined
-    case 72: return launch_t<8, 1, 3, true, false, false>(in_map, out_map, fa, s);  // no tier 1, call
     case 82: return launch_t<8, 1, 2, true>(in_map, out_map, fa, s);
     default: return launch_t<8, 1, 3, true>(in_map, out_map, fa, s);
   }
