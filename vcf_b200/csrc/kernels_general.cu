@@ -108,7 +108,9 @@ __device__ __forceinline__ unsigned warp_sum(unsigned v) {
 // encode
 // ============================================================================
 
-template <typename T, int B, bool EXACT>
+// MODE 0: subband layout, no perceptual weights, no statistics -- every flag a compile-time
+// constant; MODE 1: the same with statistics; MODE 2: everything decided at run time.
+template <typename T, int B, bool EXACT, int MODE>
 __global__ void __launch_bounds__(NT) encode_kernel(const EncArgs a) {
   using L = Layout<T, B>;
   using O = Ops<T, EXACT>;
@@ -130,9 +132,9 @@ __global__ void __launch_bounds__(NT) encode_kernel(const EncArgs a) {
   const int x0 = tile * TW;
   const int bx0 = tile * TBX;
   const int nbx = min(TBX, g.nx - bx0);
-  const bool nosub = (a.flags & VCFB_F_NO_SUBBANDS) != 0;
-  const bool percep = (a.flags & VCFB_F_PERCEPTUAL) != 0;
-  const bool do_stats = a.stats != nullptr;
+  const bool nosub = MODE == 2 && (a.flags & VCFB_F_NO_SUBBANDS) != 0;
+  const bool percep = MODE == 2 && (a.flags & VCFB_F_PERCEPTUAL) != 0;
+  const bool do_stats = MODE != 0 && a.stats != nullptr;
   const bool do_hist = do_stats && (a.flags & VCFB_F_HIST) != 0;
   const int nruns = nosub ? B : B * B;
   const int runlen = nosub ? nbx * B * 3 : nbx * 3;
@@ -326,7 +328,8 @@ __global__ void __launch_bounds__(NT) encode_kernel(const EncArgs a) {
 // decode
 // ============================================================================
 
-template <typename T, int B, bool EXACT>
+// PLAIN: subband layout and no perceptual weights, known at compile time.
+template <typename T, int B, bool EXACT, bool PLAIN>
 __global__ void __launch_bounds__(NT) decode_kernel(const DecArgs a) {
   using L = Layout<T, B>;
   using O = Ops<T, EXACT>;
@@ -349,8 +352,8 @@ __global__ void __launch_bounds__(NT) decode_kernel(const DecArgs a) {
   const int x0 = tile * TW;
   const int bx0 = tile * TBX;
   const int nbx = min(TBX, g.nx - bx0);
-  const bool nosub = (a.flags & VCFB_F_NO_SUBBANDS) != 0;
-  const bool percep = (a.flags & VCFB_F_PERCEPTUAL) != 0;
+  const bool nosub = !PLAIN && (a.flags & VCFB_F_NO_SUBBANDS) != 0;
+  const bool percep = !PLAIN && (a.flags & VCFB_F_PERCEPTUAL) != 0;
   const int nruns = nosub ? B : B * B;
   const int runlen = nosub ? nbx * B * 3 : nbx * 3;
   const int rpitch = nosub ? L::RP_NOSUB : L::RP_SUB;
@@ -504,9 +507,10 @@ __global__ void __launch_bounds__(NT) decode_kernel(const DecArgs a) {
       yo[0] = R; yo[1] = G; yo[2] = Bv;
     }
     uint8_t* o = outb + r * OUTP + oshift[r] + x * 3;
-    o[0] = uint8_t(to_int_rz<T>(fmin(fmax(R, T(0)), T(255))));
-    o[1] = uint8_t(to_int_rz<T>(fmin(fmax(G, T(0)), T(255))));
-    o[2] = uint8_t(to_int_rz<T>(fmin(fmax(Bv, T(0)), T(255))));
+    // np.clip(y, 0, 255).astype(uint8): truncation (saturating conversion) then the clip on integers
+    o[0] = uint8_t(min(max(to_int_rz<T>(R), 0), 255));
+    o[1] = uint8_t(min(max(to_int_rz<T>(G), 0), 255));
+    o[2] = uint8_t(min(max(to_int_rz<T>(Bv), 0), 255));
   }
   __syncthreads();
 
@@ -537,10 +541,39 @@ __global__ void __launch_bounds__(NT) decode_kernel(const DecArgs a) {
         }
         if (do_sse) {
           const uint8_t* op = a.original + goff - sh;
-          for (int b = vlo; b < vhi; ++b) {
-            const int d = int(op[b]) - int(sp[b]);
-            sse[(b - sh) % 3] += unsigned(d * d);
-            sdiff += d;
+          if (vlo == lo && vhi == hi) {
+            // whole 16-byte chunk: byte-wise |difference| in one instruction per word, squares summed
+            // per byte phase with a masked dp4a; phase p of the chunk is channel (p + lo - sh) mod 3
+            constexpr unsigned M[3][3] = {{0xFF0000FFu, 0x0000FF00u, 0x00FF0000u},
+                                          {0x00FF0000u, 0xFF0000FFu, 0x0000FF00u},
+                                          {0x0000FF00u, 0x00FF0000u, 0xFF0000FFu}};
+            const uint4 xo = __ldg(reinterpret_cast<const uint4*>(op + lo));
+            const uint4 yo = *reinterpret_cast<const uint4*>(sp + lo);
+            const unsigned xa[4] = {xo.x, xo.y, xo.z, xo.w}, ya[4] = {yo.x, yo.y, yo.z, yo.w};
+            unsigned ph[3] = {0, 0, 0};
+            int sx = 0, sy = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const unsigned d = __vabsdiffu4(xa[k], ya[k]);
+#pragma unroll
+              for (int p = 0; p < 3; ++p) {
+                const unsigned dm = d & M[(4 * k) % 3][p];
+                ph[p] = __dp4a(dm, dm, ph[p]);
+              }
+              sx = __dp4a(xa[k], 0x01010101u, unsigned(sx));
+              sy = __dp4a(ya[k], 0x01010101u, unsigned(sy));
+            }
+            const int rot = ((lo - sh) % 3 + 3) % 3;
+            sse[rot] += ph[0];
+            sse[rot == 2 ? 0 : rot + 1] += ph[1];
+            sse[rot == 0 ? 2 : rot - 1] += ph[2];
+            sdiff += sx - sy;
+          } else {
+            for (int b = vlo; b < vhi; ++b) {
+              const int d = int(op[b]) - int(sp[b]);
+              sse[(b - sh) % 3] += unsigned(d * d);
+              sdiff += d;
+            }
           }
         }
       }
@@ -572,10 +605,10 @@ __global__ void __launch_bounds__(NT) decode_kernel(const DecArgs a) {
 
 // ---- launchers ---------------------------------------------------------------
 
-template <typename T, int B, bool EXACT>
-int launch_enc(const EncArgs& a, cudaStream_t s) {
+template <typename T, int B, bool EXACT, int MODE>
+int launch_enc_mode(const EncArgs& a, cudaStream_t s) {
   using L = Layout<T, B>;
-  auto kern = encode_kernel<T, B, EXACT>;
+  auto kern = encode_kernel<T, B, EXACT, MODE>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::ENC_SMEM);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(encode)");
   dim3 grid((a.g.Wp + L::TW - 1) / L::TW, a.g.ny, a.n_frames);
@@ -587,9 +620,16 @@ int launch_enc(const EncArgs& a, cudaStream_t s) {
 }
 
 template <typename T, int B, bool EXACT>
-int launch_dec(const DecArgs& a, cudaStream_t s) {
+int launch_enc(const EncArgs& a, cudaStream_t s) {
+  const bool plain = !(a.flags & (VCFB_F_NO_SUBBANDS | VCFB_F_PERCEPTUAL));
+  if (EXACT && plain) return a.stats ? launch_enc_mode<T, B, EXACT, 1>(a, s) : launch_enc_mode<T, B, EXACT, 0>(a, s);
+  return launch_enc_mode<T, B, EXACT, 2>(a, s);
+}
+
+template <typename T, int B, bool EXACT, bool PLAIN>
+int launch_dec_mode(const DecArgs& a, cudaStream_t s) {
   using L = Layout<T, B>;
-  auto kern = decode_kernel<T, B, EXACT>;
+  auto kern = decode_kernel<T, B, EXACT, PLAIN>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::DEC_SMEM);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(decode)");
   dim3 grid((a.g.Wp + L::TW - 1) / L::TW, a.g.ny, a.n_frames);
@@ -598,6 +638,13 @@ int launch_dec(const DecArgs& a, cudaStream_t s) {
   e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "decode_kernel launch");
   return VCFB_OK;
+}
+
+template <typename T, int B, bool EXACT>
+int launch_dec(const DecArgs& a, cudaStream_t s) {
+  const bool plain = !(a.flags & (VCFB_F_NO_SUBBANDS | VCFB_F_PERCEPTUAL));
+  if (EXACT && plain) return launch_dec_mode<T, B, EXACT, true>(a, s);
+  return launch_dec_mode<T, B, EXACT, false>(a, s);
 }
 
 template <int B>
