@@ -152,10 +152,15 @@ int vcfb_color_decode_dev(const uint16_t* k, long long n_pixels, double q, int c
  *                         skipped, ties go to the first candidate of the dy-major scan.
  * ref, cur   (n_frames,H,W) uint8 gray frames, device; pair f is matched independently
  * mv_out     (n_frames, H/bs, W/bs, 2) int16, device: (dx, dy) as the reference stores them
- * bs a multiple of 4 in [4, 64], sr in [0, 31], H >= bs, W >= bs. */
+ * bs a multiple of 4 in [4, 64], sr in [0, 31], H >= bs, W >= bs.
+ *   vcfb_block_match_tss_dev  the `--fast` variant: `_three_step_search`, src/IPP_DCT.py:159-205, with
+ *                         its moving centre and its walk at step 1 (the vector may leave [-sr, sr]);
+ *                         bs in [1, 64], sr in [0, 32767]. */
 int vcfb_gray_dev(const uint8_t* rgb, long long n_pixels, uint8_t* gray_out, void* cuda_stream);
 int vcfb_block_match_dev(const uint8_t* ref, const uint8_t* cur, int n_frames, int H, int W, int bs, int sr,
                          int16_t* mv_out, void* cuda_stream);
+int vcfb_block_match_tss_dev(const uint8_t* ref, const uint8_t* cur, int n_frames, int H, int W, int bs, int sr,
+                             int16_t* mv_out, void* cuda_stream);
 
 /* Host-buffer convenience layer (what a numpy caller binds).  A context owns one
  * CUDA stream plus pinned and device staging buffers that grow on demand. */

@@ -55,8 +55,13 @@ def main():
             ri, row = row_fn((ref, cur, i, bs, sr, w, False))
             for col, v in enumerate(row):
                 mv[ri // bs, col] = v
-        np.savez_compressed(os.path.join(out, f"ref_me_{n}_{kind}.npz"), ref=ref, cur=cur, bs=bs, sr=sr, mv=mv)
-        print(kind, h, w, bs, sr, "->", mv.reshape(-1, 2)[:4].tolist())
+        mvf = np.zeros((h // bs, w // bs, 2), dtype=np.float32)    # the same pair with --fast (three-step search)
+        for i in range(0, h - bs + 1, bs):
+            ri, row = row_fn((ref, cur, i, bs, sr, w, True))
+            for col, v in enumerate(row):
+                mvf[ri // bs, col] = v
+        np.savez_compressed(os.path.join(out, f"ref_me_{n}_{kind}.npz"), ref=ref, cur=cur, bs=bs, sr=sr, mv=mv, mv_fast=mvf)
+        print(kind, h, w, bs, sr, "->", mv.reshape(-1, 2)[:4].tolist(), "| fast:", mvf.reshape(-1, 2)[:4].tolist())
 
 
 if __name__ == "__main__":

@@ -9,6 +9,8 @@ Follows /root/reference/src/IPP_DCT.py:
     (`IPP.block_matching`): dy-major scan of [-sr, sr]^2, out-of-frame candidates skipped,
     SAD on int16 differences, strict `<` so the first minimum of the scan wins; the field is
     float32 (h//bs, w//bs, 2) holding (dx, dy).
+  * block_matching_tss  :159-205 (`_three_step_search`, use_fast=True) driven by :212-215: the
+    centre moves inside the neighbour loop, and the step stays at 1 while rounds keep improving.
 Parity status: pinned -- tests/golden/ref_me_*.npz were produced by executing the reference's own
 `_process_block_row` (oracle/make_golden_me.py extracts it from the unmodified source file).
 """
@@ -52,4 +54,41 @@ def block_matching_full(ref_gray: np.ndarray, cur_gray: np.ndarray, bs: int, sr:
             take = ok & (sad < best)                                       # :240
             best[take] = sad[take]
             mv[take] = (dx, dy)                                            # :242
+    return mv
+
+
+def block_matching_tss(ref_gray: np.ndarray, cur_gray: np.ndarray, bs: int, sr: int) -> np.ndarray:
+    """Three-step search, block by block (plain loops: the walk is data dependent)."""
+    h, w = ref_gray.shape
+    ny, nx = h // bs, w // bs
+    ref = ref_gray.astype(np.int32)
+    cur = cur_gray.astype(np.int32)
+    mv = np.zeros((ny, nx, 2), dtype=np.float32)
+
+    def sad(block, y, x):
+        return int(np.abs(block - ref[y:y + bs, x:x + bs]).sum())
+
+    for by in range(ny):
+        for bx in range(nx):
+            i, j = by * bs, bx * bs
+            block = cur[i:i + bs, j:j + bs]
+            step = sr // 2                                        # :166
+            cx, cy, best = j, i, (0, 0)
+            min_sad = sad(block, cy, cx)                          # :171-175 (always inside the frame)
+            while step >= 1:                                      # :177
+                improved = False
+                for dy in (-step, 0, step):                       # :180-181
+                    for dx in (-step, 0, step):
+                        if dy == 0 and dx == 0:
+                            continue
+                        ry, rx = cy + dy, cx + dx                 # :185-186: the centre may already have moved
+                        if ry < 0 or ry + bs > h or rx < 0 or rx + bs > w:
+                            continue
+                        s_ = sad(block, ry, rx)
+                        if s_ < min_sad:                          # :193
+                            min_sad, best = s_, (rx - j, ry - i)
+                            cx, cy = rx, ry
+                            improved = True
+                step = max(1, step // 2) if improved else step // 2   # :199-202
+            mv[by, bx] = best
     return mv

@@ -20,6 +20,8 @@ def test_oracle_matches_reference_vectors(fn):
     g = np.load(fn)
     mv = M.block_matching_full(g["ref"], g["cur"], int(g["bs"]), int(g["sr"]))
     assert mv.dtype == np.float32 and np.array_equal(mv, g["mv"])
+    mvf = M.block_matching_tss(g["ref"], g["cur"], int(g["bs"]), int(g["sr"]))
+    assert mvf.dtype == np.float32 and np.array_equal(mvf, g["mv_fast"])
 
 
 def test_gray_fixed_point_is_opencv():
@@ -44,6 +46,9 @@ def test_gpu_block_matching_matches_reference_vectors(fn):
     mv = block_matching(g["ref"], g["cur"], int(g["bs"]), int(g["sr"]))
     assert _lib.last_kernel() == "block_match"
     assert mv.dtype == np.float32 and np.array_equal(mv, g["mv"])
+    mvf = block_matching(g["ref"], g["cur"], int(g["bs"]), int(g["sr"]), use_fast=True)
+    assert _lib.last_kernel() == "block_match_tss"
+    assert np.array_equal(mvf, g["mv_fast"])
 
 
 @pytest.mark.gpu
@@ -63,6 +68,8 @@ def test_gpu_block_matching_against_oracle():
         want = M.block_matching_full(rg, cg, bs, sr)
         got = block_matching(ref, cur, bs, sr)          # RGB in: gray conversion on the GPU
         assert np.array_equal(got, want), (h, w, bs, sr)
+        if h * w <= 16384:                              # the loop-form oracle of the three-step search is slow
+            assert np.array_equal(block_matching(rg, cg, bs, sr, use_fast=True), M.block_matching_tss(rg, cg, bs, sr)), (h, w, bs, sr)
         got2 = block_matching(torch.from_numpy(np.stack([rg, cg])).cuda(), torch.from_numpy(np.stack([cg, rg])).cuda(), bs, sr)
         assert np.array_equal(got2[0].cpu().numpy(), want)
         assert np.array_equal(got2[1].cpu().numpy(), M.block_matching_full(cg, rg, bs, sr))

@@ -73,6 +73,8 @@ def lib():
     L.vcfb_gray_dev.restype = i
     L.vcfb_block_match_dev.argtypes = [vp, vp, i, i, i, i, i, vp, vp]
     L.vcfb_block_match_dev.restype = i
+    L.vcfb_block_match_tss_dev.argtypes = [vp, vp, i, i, i, i, i, vp, vp]
+    L.vcfb_block_match_tss_dev.restype = i
     _lib = L
     return L
 

@@ -176,6 +176,16 @@ int vcfb_block_match_dev(const uint8_t* ref, const uint8_t* cur, int n_frames, i
   return launch_block_match(ref, cur, n_frames, H, W, bs, sr, mv_out, static_cast<cudaStream_t>(cuda_stream));
 }
 
+int vcfb_block_match_tss_dev(const uint8_t* ref, const uint8_t* cur, int n_frames, int H, int W, int bs, int sr,
+                             int16_t* mv_out, void* cuda_stream) {
+  if (!ref || !cur || !mv_out) { set_error("NULL pointer"); return VCFB_E_ARG; }
+  if (n_frames <= 0 || n_frames > 65535) { set_error("n_frames must be in [1, 65535]"); return VCFB_E_ARG; }
+  if (bs < 1 || bs > 64) { set_error("motion block size must be in [1, 64]"); return VCFB_E_ARG; }
+  if (sr < 0 || sr > 32767) { set_error("search range must be in [0, 32767]"); return VCFB_E_ARG; }
+  if (H < bs || W < bs || H > 32767 || W > 32767) { set_error("frame smaller than one motion block (or larger than 32767)"); return VCFB_E_ARG; }
+  return launch_block_match_tss(ref, cur, n_frames, H, W, bs, sr, mv_out, static_cast<cudaStream_t>(cuda_stream));
+}
+
 // ---- host-buffer layer ----------------------------------------------------------
 //
 // A batch is cut into chunks of whole frames; chunk i runs on slot i % NSLOT

@@ -73,5 +73,7 @@ int launch_color_decode(const uint16_t* k, long long npx, double q, int color, u
 int launch_gray(const uint8_t* rgb, long long npx, uint8_t* gray, cudaStream_t s);
 int launch_block_match(const uint8_t* ref, const uint8_t* cur, int n_frames, int H, int W, int bs, int sr, short* mv,
                        cudaStream_t s);
+int launch_block_match_tss(const uint8_t* ref, const uint8_t* cur, int n_frames, int H, int W, int bs, int sr, short* mv,
+                           cudaStream_t s);
 
 }  // namespace vcfb

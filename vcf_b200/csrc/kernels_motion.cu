@@ -91,6 +91,70 @@ block_match_kernel(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ 
   }
 }
 
+// Three-step search of src/IPP_DCT.py:159-205 (`_three_step_search`), one warp per block, every
+// quirk kept: the centre moves as soon as a neighbour improves the SAD, so the remaining
+// neighbours of the same round are taken around the NEW centre; after a round with an
+// improvement the step is max(1, step // 2), so the search keeps walking with step 1 until a
+// round brings nothing -- the vector is not confined to the search range.  The reference frame
+// is read from global memory (the walk has no fixed window).
+__device__ __forceinline__ unsigned warp_sad(const uint8_t* __restrict__ cb, const uint8_t* __restrict__ rf, int W, int bs,
+                                             int cy, int cx, int lane) {
+  unsigned sad = 0;
+  for (int p = lane; p < bs * bs; p += 32) {
+    const int y = p / bs, x = p - y * bs;
+    sad += __sad(int(cb[y * bs + x]), int(rf[(size_t)(cy + y) * W + cx + x]), 0u);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sad += __shfl_xor_sync(0xffffffffu, sad, o);
+  return sad;
+}
+
+__global__ void __launch_bounds__(128)
+tss_kernel(const uint8_t* __restrict__ ref, const uint8_t* __restrict__ cur, int H, int W, int bs, int sr, int nbx,
+           int nby, int n_frames, short* __restrict__ mv) {
+  extern __shared__ unsigned char sm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned char* cb = sm + warp * bs * bs;            // the current block of this warp
+  const long long nblk = (long long)n_frames * nby * nbx;
+  for (long long blk = (long long)blockIdx.x * 4 + warp; blk < nblk; blk += (long long)gridDim.x * 4) {
+    const int f = int(blk / ((long long)nby * nbx));
+    const int rem = int(blk - (long long)f * nby * nbx);
+    const int by = rem / nbx, bx = rem - by * nbx;
+    const int i = by * bs, j = bx * bs;
+    const uint8_t* rf = ref + (size_t)f * H * W;
+    const uint8_t* cf = cur + (size_t)f * H * W;
+    __syncwarp();
+    for (int p = lane; p < bs * bs; p += 32) cb[p] = cf[(size_t)(i + p / bs) * W + j + p % bs];
+    __syncwarp();
+    int step = sr / 2, cx = j, cy = i, bdx = 0, bdy = 0;
+    unsigned min_sad = warp_sad(cb, rf, W, bs, cy, cx, lane);       // the block position itself is always inside
+    while (step >= 1) {
+      bool improved = false;
+      for (int a = -1; a <= 1; ++a)
+        for (int b = -1; b <= 1; ++b) {
+          if (a == 0 && b == 0) continue;
+          const int ry = cy + a * step, rx = cx + b * step;          // around the centre as it is NOW
+          if (ry < 0 || ry + bs > H || rx < 0 || rx + bs > W) continue;
+          const unsigned sad = warp_sad(cb, rf, W, bs, ry, rx, lane);
+          if (sad < min_sad) {
+            min_sad = sad;
+            bdx = rx - j;
+            bdy = ry - i;
+            cx = rx;
+            cy = ry;
+            improved = true;
+          }
+        }
+      step = improved ? max(1, step / 2) : step / 2;
+    }
+    if (lane == 0) {
+      short* o = mv + blk * 2;
+      o[0] = short(bdx);
+      o[1] = short(bdy);
+    }
+  }
+}
+
 }  // namespace
 
 int launch_gray(const uint8_t* rgb, long long npx, uint8_t* gray, cudaStream_t s) {
@@ -112,6 +176,19 @@ int launch_block_match(const uint8_t* ref, const uint8_t* cur, int n_frames, int
   block_match_kernel<<<grid, ME_THREADS, smem, s>>>(ref, cur, H, W, bs, sr, mv);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "block_match_kernel launch");
+  return VCFB_OK;
+}
+
+int launch_block_match_tss(const uint8_t* ref, const uint8_t* cur, int n_frames, int H, int W, int bs, int sr, short* mv,
+                           cudaStream_t s) {
+  const int nbx = W / bs, nby = H / bs;
+  const long long nblk = (long long)n_frames * nby * nbx;
+  long long grid = (nblk + 3) / 4;
+  if (grid > 148 * 16) grid = 148 * 16;
+  note_kernel("block_match_tss");
+  tss_kernel<<<int(grid), 128, 4 * bs * bs, s>>>(ref, cur, H, W, bs, sr, nbx, nby, n_frames, mv);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "tss_kernel launch");
   return VCFB_OK;
 }
 

@@ -46,8 +46,10 @@ def rgb_to_gray(frame):
     return _gray_dev(torch, torch.from_numpy(np.ascontiguousarray(frame)).cuda()).cpu().numpy()
 
 
-def block_matching(ref_frame, curr_frame, block_size: int = 16, search_range: int = 8, color: bool | None = None):
-    """Full-search motion vectors of ``curr_frame`` against ``ref_frame``.
+def block_matching(ref_frame, curr_frame, block_size: int = 16, search_range: int = 8, color: bool | None = None,
+                   use_fast: bool = False):
+    """Motion vectors of ``curr_frame`` against ``ref_frame``: full search, or with ``use_fast``
+    the three-step search of ``_three_step_search`` (src/IPP_DCT.py:159-205, the ``--fast`` flag).
 
     Frames: uint8, gray ``(H, W)`` / ``(n, H, W)`` or RGB ``(H, W, 3)`` / ``(n, H, W, 3)``
     (``color`` overrides the guess "last dimension == 3 means RGB")."""
@@ -75,8 +77,8 @@ def block_matching(ref_frame, curr_frame, block_size: int = 16, search_range: in
     bs, sr = int(block_size), int(search_range)
     mv = torch.empty((n, H // bs if H >= bs else 0, W // bs if W >= bs else 0, 2), dtype=torch.int16, device=r.device)
     with torch.cuda.device(r.device):
-        check(_lib.lib().vcfb_block_match_dev(r.data_ptr(), c.data_ptr(), n, H, W, bs, sr, mv.data_ptr(),
-                                              torch.cuda.current_stream().cuda_stream))
+        fn = _lib.lib().vcfb_block_match_tss_dev if use_fast else _lib.lib().vcfb_block_match_dev
+        check(fn(r.data_ptr(), c.data_ptr(), n, H, W, bs, sr, mv.data_ptr(), torch.cuda.current_stream().cuda_stream))
     mv = mv.to(torch.float32)                      # the reference's field is float32 (:354)
     if not batched:
         mv = mv[0]

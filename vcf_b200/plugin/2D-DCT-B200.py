@@ -49,7 +49,7 @@ for _p in (parser.parser_encode, parser.parser_decode):
     _p.add_argument("-p", "--perceptual_quantization", action='store_true', help="weight the coefficients with the JPEG luma / chroma tables before quantising", default=perceptual_quantization)
     _p.add_argument("-x", "--disable_subbands", action='store_true', help="keep the coefficients in block order instead of grouping them by subband", default=disable_subbands)
 parser.parser_encode.add_argument("-L", "--Lambda", type=parser.int_or_str, help="when given (float): pick the block size in {4, 8, 16, 32} minimising bytes + Lambda * RMSE")
-parser.parser_decode.add_argument("--b200_fast_decode", action='store_true', help="float32 GPU decoder (pixels within +-1 of the reference) instead of the bit-exact float64 one", default=False)
+parser.parser_decode.add_argument("--b200_fast_decode", action='store_true', help="float32 GPU decoder (pixels within +-1 of the reference, PSNR within 0.01 dB) instead of the bit-exact float64 one", default=False)
 
 args = parser.parser.parse_known_args()[0]
 CT = importlib.import_module(args.color_transform)
