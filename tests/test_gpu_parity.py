@@ -266,6 +266,34 @@ def test_fast_encode_path_exact(q, torch_cuda):
     assert np.array_equal(got.cpu().numpy(), O.encode_array(img, 8, q))
 
 
+@pytest.mark.parametrize("color", ["YCoCg", "YCrCb"])
+@pytest.mark.parametrize("q", [1, 8, 12, 32, 100])
+def test_fast16_encode_path_exact(q, color, torch_cuda):
+    """B = 16 fast path (kernels_b16.cu): bit-exact indices and statistics, both colour
+    transforms, batches, vertical padding (TMA zero fill), widths that are multiples of 256."""
+    from vcf_b200 import _lib
+    from vcf_b200.codec import stats_dict
+    t = torch_cuda
+    for si, (H, W) in enumerate(((16, 256), (48, 512), (40, 768), (64, 1280), (272, 3840))):
+        n = 3 if H * W < 100000 else 1
+        frames = np.stack([O.synthetic_frame(H, W, 1500 + 10 * si + i, "noise" if i % 2 else "natural") for i in range(n)])
+        ref = np.stack([O.encode_array(f, 16, q, color=color) for f in frames])
+        enc = _codec(block_size=16, q=q, color=color, hist=False)
+        got, st = enc.encode(t.from_numpy(frames).cuda(), stats=True)
+        assert _lib.last_kernel() == "enc16_fast", (H, W, _lib.last_kernel())
+        assert np.array_equal(got.cpu().numpy(), ref), (H, W, q, color, int((got.cpu().numpy() != ref).sum()))
+        nz, sabs, _ = O.index_stats(ref)
+        s = stats_dict(st.cpu().numpy())
+        assert s["nonzero"] == nz and s["sumabs"] == sabs and s["nindices"] == ref.size
+        got2 = enc.encode(t.from_numpy(frames).cuda())
+        assert np.array_equal(got2.cpu().numpy(), ref)
+    # a width that is not a multiple of 256 takes the general kernel
+    img = O.synthetic_frame(32, 320, 3, "natural")
+    got = _codec(block_size=16, q=q, color=color).encode(t.from_numpy(img).cuda())
+    assert _lib.last_kernel() == "encode_general"
+    assert np.array_equal(got.cpu().numpy(), O.encode_array(img, 16, q, color=color))
+
+
 @pytest.mark.parametrize("q", [1, 8, 12, 32, 64, 255])
 def test_fast_decode_path(q, torch_cuda):
     """TMA decode fast path: float64 mode bit-exact with the reference chain, float32

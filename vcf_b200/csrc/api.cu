@@ -108,7 +108,8 @@ int vcfb_encode_dev(const uint8_t* rgb, int n_frames, int H, int W, int B, doubl
   a.flags = flags;
   a.weights = weights;
   a.stats = reinterpret_cast<unsigned long long*>(stats);
-  rc = launch_encode_fast(a, B, static_cast<cudaStream_t>(cuda_stream));
+  rc = B == 16 ? launch_encode_fast16(a, static_cast<cudaStream_t>(cuda_stream))
+               : launch_encode_fast(a, B, static_cast<cudaStream_t>(cuda_stream));
   if (rc != VCFB_E_UNSUPP) return rc;
   return launch_encode_general(a, B, static_cast<cudaStream_t>(cuda_stream));
 }

@@ -58,6 +58,8 @@ int launch_decode_general(const DecArgs& a, int B, cudaStream_t s);
 // fast path (kernels_fast.cu): VCFB_E_UNSUPP means "not covered, use the general kernel"
 int launch_encode_fast(const EncArgs& a, int B, cudaStream_t s);
 int launch_decode_fast(const DecArgs& a, int B, cudaStream_t s);
+// B = 16 fast path (kernels_b16.cu)
+int launch_encode_fast16(const EncArgs& a, cudaStream_t s);
 
 // streaming statistics behind the fast path (kernels_stats.cu); VCFB_E_UNSUPP if unaligned
 int launch_index_stats(const uint8_t* idx, long long n_bytes, bool hist, unsigned long long* stats, cudaStream_t s);
