@@ -294,6 +294,42 @@ def test_fast16_encode_path_exact(q, color, torch_cuda):
     assert np.array_equal(got.cpu().numpy(), O.encode_array(img, 16, q, color=color))
 
 
+@pytest.mark.parametrize("color", ["YCoCg", "YCrCb"])
+@pytest.mark.parametrize("q", [1, 8, 12, 32, 255])
+def test_fast16_decode_path_exact(q, color, torch_cuda):
+    """B = 16 fast path, float64 decoder: bit-exact pixels and distortion statistics, both colour
+    transforms, batches, arbitrary (non-encoder) index arrays."""
+    from vcf_b200 import _lib
+    from vcf_b200.codec import stats_dict
+    t = torch_cuda
+    rng = np.random.default_rng(q)
+    for si, (H, W) in enumerate(((16, 256), (48, 512), (64, 768), (272, 3840))):
+        n = 3 if H * W < 100000 else 1
+        frames = np.stack([O.synthetic_frame(H, W, 1600 + 10 * si + i, "noise" if i % 2 else "natural") for i in range(n)])
+        idx = np.stack([O.encode_array(f, 16, q, color=color) for f in frames])
+        if si % 2:
+            idx[-1] = rng.integers(0, 256, size=idx[-1].shape, dtype=np.uint8)
+        ref = np.stack([O.decode_array(k, (H, W, 3), 16, q, color=color) for k in idx])
+        dec = _codec(block_size=16, q=q, color=color, fp64=True)
+        x = t.from_numpy(frames).cuda()
+        got, st = dec.decode(t.from_numpy(idx).cuda(), (H, W), original=x, stats=True)
+        assert _lib.last_kernel() == "dec16_fast", (H, W, _lib.last_kernel())
+        assert np.array_equal(got.cpu().numpy(), ref), (H, W, q, color, int((got.cpu().numpy() != ref).sum()))
+        s = stats_dict(st.cpu().numpy())
+        for c in range(3):
+            assert int(s["sse"][c]) == O.sse_int(frames[..., c], ref[..., c])
+        assert s["nsamples"] == frames.size
+        assert s["sumdiff"] == int((frames.astype(np.int64) - ref.astype(np.int64)).sum())
+        got2 = dec.decode(t.from_numpy(idx).cuda(), (H, W))
+        assert np.array_equal(got2.cpu().numpy(), ref)
+    # vertical padding takes the general kernel
+    img = O.synthetic_frame(40, 256, 3, "natural")
+    k = O.encode_array(img, 16, q, color=color)
+    got = _codec(block_size=16, q=q, color=color, fp64=True).decode(t.from_numpy(k).cuda(), (40, 256))
+    assert _lib.last_kernel() == "decode_general"
+    assert np.array_equal(got.cpu().numpy(), O.decode_array(k, img.shape, 16, q, color=color))
+
+
 @pytest.mark.parametrize("q", [1, 8, 12, 32, 64, 255])
 def test_fast_decode_path(q, torch_cuda):
     """TMA decode fast path: float64 mode bit-exact with the reference chain, float32

@@ -138,7 +138,8 @@ int vcfb_decode_dev(const uint8_t* idx, int n_frames, int H, int W, int B, doubl
   a.flags = flags;
   a.weights = weights;
   a.stats = reinterpret_cast<unsigned long long*>(stats);
-  rc = launch_decode_fast(a, B, static_cast<cudaStream_t>(cuda_stream));
+  rc = B == 16 ? launch_decode_fast16(a, static_cast<cudaStream_t>(cuda_stream))
+               : launch_decode_fast(a, B, static_cast<cudaStream_t>(cuda_stream));
   if (rc != VCFB_E_UNSUPP) return rc;
   return launch_decode_general(a, B, static_cast<cudaStream_t>(cuda_stream));
 }
