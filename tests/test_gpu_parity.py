@@ -287,6 +287,12 @@ def test_fast16_encode_path_exact(q, color, torch_cuda):
         assert s["nonzero"] == nz and s["sumabs"] == sabs and s["nindices"] == ref.size
         got2 = enc.encode(t.from_numpy(frames).cuda())
         assert np.array_equal(got2.cpu().numpy(), ref)
+        if si == 1:          # with the histogram: fast kernel + streaming pass over the indices
+            got3, st3 = _codec(block_size=16, q=q, color=color, hist=True).encode(t.from_numpy(frames).cuda(), stats=True)
+            assert _lib.last_kernel() == "enc16_fast"
+            s3 = stats_dict(st3.cpu().numpy())
+            assert np.array_equal(got3.cpu().numpy(), ref) and np.array_equal(s3["hist"], O.index_stats(ref)[2])
+            assert s3["nonzero"] == nz and s3["sumabs"] == sabs and s3["nindices"] == ref.size
     # a width that is not a multiple of 256 takes the general kernel
     img = O.synthetic_frame(32, 320, 3, "natural")
     got = _codec(block_size=16, q=q, color=color).encode(t.from_numpy(img).cuda())

@@ -519,9 +519,18 @@ int launch_dec16(const CUtensorMap& in_map, const CUtensorMap& out_map, const De
 // Returns VCFB_E_UNSUPP when the request is outside this fast path (the caller then uses the
 // general kernel), VCFB_OK after a launch, or an error.
 int launch_encode_fast16(const EncArgs& a, cudaStream_t s) {
-  if (a.flags & (VCFB_F_NO_SUBBANDS | VCFB_F_PERCEPTUAL | VCFB_F_FP64 | VCFB_F_CONTRACT | VCFB_F_HIST)) return VCFB_E_UNSUPP;
+  if (a.flags & (VCFB_F_NO_SUBBANDS | VCFB_F_PERCEPTUAL | VCFB_F_FP64 | VCFB_F_CONTRACT)) return VCFB_E_UNSUPP;
   if (getenv("VCFB_NO_FAST16")) return VCFB_E_UNSUPP;          // development knob
   const Geom& g = a.g;
+  if (a.stats && (a.flags & VCFB_F_HIST)) {
+    // the histogram takes the streaming pass over the stored indices (kernels_stats.cu)
+    if (reinterpret_cast<uintptr_t>(a.idx) & 15) return VCFB_E_UNSUPP;
+    EncArgs b = a;
+    b.stats = nullptr;
+    int rc = launch_encode_fast16(b, s);
+    if (rc) return rc;
+    return launch_index_stats(a.idx, (long long)a.n_frames * g.Hp * g.Wp * 3, true, a.stats, s);
+  }
   if (g.W % T16_W != 0 || g.left != 0 || g.nx % 16 != 0) return VCFB_E_UNSUPP;
   if ((reinterpret_cast<uintptr_t>(a.rgb) & 15) || (reinterpret_cast<uintptr_t>(a.idx) & 15)) return VCFB_E_UNSUPP;
   if (!tma::encode_tiled_fn()) return VCFB_E_UNSUPP;

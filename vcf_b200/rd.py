@@ -27,7 +27,9 @@ def rd_point(frames, block_size: int, q, compress: Optional[Callable] = None, **
     dec = Codec(block_size=block_size, q=q, fp64=True, **{k: v for k, v in codec_kw.items() if k != "contract"})
     idx, s_enc = enc.encode(frames, stats=True)
     shape = frames.shape[-3:-1]
-    out = dec.decode(idx, shape, original=frames, stats=True, want_rgb=False)
+    # (the decoded frames are written although only the statistics are used: the TMA fast paths
+    #  always produce them, and they are several times faster than the general kernels that can skip them)
+    out = dec.decode(idx, shape, original=frames, stats=True)
     s_dec = out[-1]
     if _is_torch(frames):
         st = stats_dict((s_enc + s_dec).cpu().numpy())
