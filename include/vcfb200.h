@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define VCFB_VERSION 100 /* 0.1.0 */
+#define VCFB_VERSION 110 /* 0.1.1: + vcfb_launch_count, vcfb_gray_dev, vcfb_block_match_dev, vcfb_block_match_tss_dev */
 
 /* error codes */
 #define VCFB_OK 0
