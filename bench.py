@@ -375,6 +375,27 @@ def run_ours(a):
                      "tolerance": "pixels within +-1 LSB of the reference, PSNR within 0.01 dB",
                      "max_abs_diff_vs_exact_decoder_last_step": dmax}
 
+    # ---- single-frame latency, frame resident in HBM (SURVEY.md 8d "Method") ----------------
+    latency = None
+    if not rde:
+        x1, i1_, y1 = x[:1], idx[:1], y[:1]
+        reps = 20
+        for q in QS:
+            enc[q].encode(x1, out=i1_)
+            dec[q].decode(i1_, (H, W), out=y1)
+        torch.cuda.synchronize()
+        le = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        le[0].record()
+        for r in range(reps):
+            enc[QS[r % NQ]].encode(x1, out=i1_)
+        le[1].record()
+        for r in range(reps):
+            dec[QS[r % NQ]].decode(i1_, (H, W), out=y1)
+        le[2].record()
+        torch.cuda.synchronize()
+        latency = {"encode_ms": le[0].elapsed_time(le[1]) / reps, "decode_ms": le[1].elapsed_time(le[2]) / reps,
+                   "note": "one frame per call, back-to-back launches on one stream, q cycled; decode includes the probe"}
+
     # ---- end to end through the host API: pinned numpy in, pinned numpy out ----------
     ne = a.e2e_frames
     hx = torch.empty((ne, H, W, 3), dtype=torch.uint8, pin_memory=True)
@@ -456,6 +477,8 @@ def run_ours(a):
             "roofline": roofline}
     if fast_mode:
         line["fast_mode"] = fast_mode
+    if latency:
+        line["single_frame_latency"] = latency
     if world == 1 and not a.no_cpu_baseline:
         line["cpu_baseline"] = cpu_oracle_throughput(a.cpu_seconds)
     print(json.dumps(line))

@@ -254,9 +254,6 @@ template <typename T> __device__ __forceinline__ int trunc_to_int(T x);
 template <> __device__ __forceinline__ int trunc_to_int<float>(float x) { return __float2int_rz(x); }
 template <> __device__ __forceinline__ int trunc_to_int<double>(double x) { return __double2int_rz(x); }
 
-template <typename T> struct Vec;   // 16-byte vector of T
-template <> struct Vec<float> { using type = float4; static constexpr int N = 4; };
-template <> struct Vec<double> { using type = double2; static constexpr int N = 2; };
 
 template <typename T, bool EXACT, int NWARPS, int CTAS>
 __global__ void __launch_bounds__(NWARPS * 32, CTAS)
@@ -499,7 +496,6 @@ dec8_f64h_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_consta
   const int i1 = lane & 7, G1 = lane >> 3;     // pass 1
   const int G2 = lane & 3, y2 = lane >> 2;     // pass 2
   const int q = a.q;
-  const int qbias = int(0x80000000u) - 128 * q;
   const int woff = (6 * G1) >> 2;              // word of the first byte of the lane's 6-byte run
   const int sh0 = ((6 * G1) & 3) * 8;          // bit offset inside that word (0 or 16)
   constexpr T SCALE = T(p2(2 * M8I::exp(0)));

@@ -92,10 +92,6 @@ __device__ __forceinline__ T color_fwd(int color, int c, int R, int G, int Bc) {
   return O::mul(O::sub(b, y), T(0.564));
 }
 
-__device__ __forceinline__ int color_exp(int color, int c) {
-  return color == VCFB_COLOR_YCOCG ? (c == 1 ? -1 : -2) : 0;
-}
-
 // ---- small helpers ----------------------------------------------------------
 
 __device__ __forceinline__ unsigned warp_sum(unsigned v) {
