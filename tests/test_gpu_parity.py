@@ -398,6 +398,21 @@ def _crafted_indices(rng, H, W, kind):
             else:                # rational positions only
                 ks[j, 4, 0, 0] = v; ks[j, 0, 4, 1] = -v; ks[j, 4, 4, 2] = v
         k[sparse] = ks
+    elif kind in ("low2", "low4", "low24", "low42"):
+        # non-zero indices only in the first 2 / 4 coefficient rows and columns: the pruned
+        # codelets (dct8_inv_low2 / _low4) of the exact decoder, every row/column combination
+        nu, ni = {"low2": (2, 2), "low4": (4, 4), "low24": (2, 4), "low42": (4, 2)}[kind]
+        k[:, :, :nu, :ni, :] = rng.integers(-9, 10, size=(ny, nx, nu, ni, 3))
+        k[:, : nx // 2, :, :, 1] = 0                             # a channel without AC in half of the tiles
+        k[:, : nx // 2, 0, 0, 1] = rng.integers(-40, 41, size=(ny, nx // 2))
+    elif kind == "lowmix":
+        # the extent of the non-zero indices changes from one group of 8 blocks to the next, so
+        # consecutive half-tiles of a warp take different codelet variants (stale intermediates of a
+        # previous half-tile must never be read)
+        for by in range(ny):
+            for g0 in range(0, nx, 8):
+                nu, ni = int(rng.choice([1, 2, 3, 4, 6, 8])), int(rng.choice([1, 2, 3, 4, 6, 8]))
+                k[by, g0:g0 + 8, :nu, :ni, :] = rng.integers(-9, 10, size=(min(8, nx - g0), nu, ni, 3))
     elif kind == "rowwise":
         # long DC-only runs interrupted by single dense blocks: partially DC-only half-tiles
         hit = rng.random((ny, nx)) < 0.04
@@ -407,7 +422,7 @@ def _crafted_indices(rng, H, W, kind):
 
 
 @pytest.mark.parametrize("cfg", ["8x1", "9x1", "4x3"], ids=["two_tier", "exact_dcskip", "two_tier_12warps"])
-@pytest.mark.parametrize("kind", ["dc", "dc_extreme", "mixed", "rowwise"])
+@pytest.mark.parametrize("kind", ["dc", "dc_extreme", "mixed", "rowwise", "low2", "low4", "low24", "low42", "lowmix"])
 def test_two_tier_decode_branches(kind, cfg, torch_cuda, monkeypatch):
     """Every branch of kernels_dec2t.cu (and the DC-only shortcut of the exact kernel) against the
     oracle's float64 chain, bit for bit.  The decoder is forced: at these sizes the library would

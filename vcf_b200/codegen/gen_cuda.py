@@ -99,6 +99,96 @@ def emit_codelet(n: int, inverse: bool) -> str:
     return "\n".join(L)
 
 
+def emit_pruned_codelet(n: int, inverse: bool, nin: int) -> str:
+    """The same program with inputs nin..n-1 known to be exact zeros.  Every operation that has a
+    zero operand is exact (x + 0 = x, 0 * c = 0, a * 2^k + 0 = a * 2^k), so dropping it changes
+    no bit of any non-zero value (only the sign of an exact zero can differ, which no later
+    operation turns into a different non-zero value).  Same output scaling as the full codelet."""
+    g, outs = D.trace_dct(n, inverse)
+    live = D.live_nodes(g, outs)
+    name = f"dct{n}_{'inv' if inverse else 'fwd'}_low{nin}"
+    L = []
+    ZERO = None
+    form = {}            # node -> None (exact zero) | (expression name, sign)
+    nops = 0
+
+    def emit(idx, expr):
+        nonlocal nops
+        nops += 1
+        L.append(f"  const T t{idx} = {expr};")
+        return f"t{idx}"
+
+    def addsub(idx, x, y):          # value of x + y for resolved operands (name, sign)
+        (xn, xs), (yn, ys) = x, y
+        if xs > 0 and ys > 0:
+            return (emit(idx, f"O::add({xn}, {yn})"), 1)
+        if xs > 0 and ys < 0:
+            return (emit(idx, f"O::sub({xn}, {yn})"), 1)
+        if xs < 0 and ys > 0:
+            return (emit(idx, f"O::sub({yn}, {xn})"), 1)
+        return (emit(idx, f"O::add({xn}, {yn})"), -1)      # (-x) + (-y) = -(x + y), exactly
+
+    for idx, nd in enumerate(g.nodes):
+        if idx not in live:
+            continue
+        op = nd[0]
+        if op == "in":
+            if nd[1] >= nin:
+                form[idx] = ZERO
+            else:
+                L.append(f"  const T i{nd[1]} = v[{nd[1]}];")
+                form[idx] = (f"i{nd[1]}", 1)
+        elif op in ("add", "sub"):
+            a, b = form[nd[1]], form[nd[2]]
+            if op == "sub" and b is not ZERO:
+                b = (b[0], -b[1])
+            if a is ZERO and b is ZERO:
+                form[idx] = ZERO
+            elif a is ZERO:
+                form[idx] = b
+            elif b is ZERO:
+                form[idx] = a
+            else:
+                form[idx] = addsub(idx, a, b)
+        elif op == "mul":
+            a = form[nd[1]]
+            form[idx] = ZERO if a is ZERO else (emit(idx, f"O::mul({a[0]}, {_const(nd[2])})"), a[1])
+        elif op == "fma2":
+            _, a, k, b, sa, sb = nd
+            fa, fb = form[a], form[b]
+            if fa is ZERO and fb is ZERO:
+                form[idx] = ZERO
+            elif fa is ZERO:
+                form[idx] = (fb[0], fb[1] * (1 if sb > 0 else -1))
+            else:
+                cv = (-1.0 if sa * fa[1] < 0 else 1.0) * float(2.0 ** k)
+                c = f"vcfb::konst<T>({cv!r}f, {cv!r})"
+                if fb is ZERO:
+                    form[idx] = (emit(idx, f"O::mul({fa[0]}, {c})"), 1)         # exact: power of two
+                else:
+                    bb = fb[0] if sb * fb[1] > 0 else f"O::neg({fb[0]})"
+                    form[idx] = (emit(idx, f"O::fma({fa[0]}, {c}, {bb})"), 1)
+    body = L
+    H = [f"// {name}: inputs {nin}..{n - 1} are exact zeros -- {nops} operations",
+         "template <typename T, bool EXACT>",
+         f"__device__ __forceinline__ void {name}(T (&v)[{n}]) {{",
+         "  using O = vcfb::Ops<T, EXACT>;"]
+    T = []
+    for k, o in enumerate(outs):
+        f = form[o.node]
+        if f is ZERO:
+            T.append(f"  v[{k}] = T(0);")
+        elif f[1] > 0:
+            T.append(f"  v[{k}] = {f[0]};")
+        else:
+            T.append(f"  v[{k}] = O::neg({f[0]});")
+    return "\n".join(H + body + T + ["}"])
+
+
+# pruned variants emitted: (n, inverse, number of leading inputs that may be non-zero)
+PRUNED = ((8, True, 2), (8, True, 4))
+
+
 def generate() -> str:
     parts = [
         "// GENERATED by vcf_b200/codegen/gen_cuda.py -- do not edit.",
@@ -114,6 +204,9 @@ def generate() -> str:
         for inv in (False, True):
             parts.append(emit_codelet(n, inv))
             parts.append("")
+    for n, inv, nin in PRUNED:
+        parts.append(emit_pruned_codelet(n, inv, nin))
+        parts.append("")
     # dispatcher
     parts.append("template <int N, bool INV> struct Dct;")
     for n in SIZES:

@@ -20,6 +20,7 @@
 //     32-bit words into the dense TMA store box [j][i][block*3+c];
 //   * every shared-memory offset is a compile-time immediate on a per-thread base.
 #include <mutex>
+#include <type_traits>
 
 #include "fast_common.cuh"
 #include "dec8_dc.cuh"
@@ -533,27 +534,34 @@ dec8_f64h_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_consta
         }
     }
     __syncwarp();
-    // Which channels carry AC indices, per half-tile (bit 3h + c).  A channel without any is not
-    // transformed: every sample of block b equals (q k_b c0) c0 exactly (dec8_dc.cuh) -- smooth
-    // content at a coarse step, and the chroma planes of most natural content from q ~ 24 up.
-    unsigned chan6 = 0x3fu;
+    // Per half-tile: which channels carry AC indices (bits 16..18), which coefficient rows u
+    // (bits 0..7) and columns i (bits 8..15) hold any non-zero index.  A channel without AC indices
+    // is not transformed -- every sample of block b equals (q k_b c0) c0 exactly (dec8_dc.cuh): smooth
+    // content at a coarse step, the chroma planes of most natural content from q ~ 24 up.  Rows /
+    // columns beyond the first 2 or 4 that are zero throughout select the pruned codelets
+    // (dct8_inv_low2 / _low4: the same operations minus those on exact zeros).
+    unsigned cls[2] = {0x7ffffu, 0x7ffffu};
     if (DCSKIP) {
-      unsigned f6 = 0;
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         uint32_t nz0 = (wd[h][0][0] ^ 0x80808080u) & dcm, nz1 = (wd[h][0][1] ^ 0x80808080u) & dcm;
+        unsigned rows = 1u;                       // row 0 holds the DC indices
 #pragma unroll
         for (int uu = 1; uu < 8; ++uu) {
-          nz0 |= wd[h][uu][0] ^ 0x80808080u;
-          nz1 |= wd[h][uu][1] ^ 0x80808080u;
+          const uint32_t t0 = wd[h][uu][0] ^ 0x80808080u, t1 = wd[h][uu][1] ^ 0x80808080u;
+          nz0 |= t0;
+          nz1 |= t1;
+          rows |= ((t0 | t1) ? 1u : 0u) << uu;    // whole words: neighbours of the same half-tile included
         }
+        const unsigned col = (i1 == 0 || ((nz0 | nz1) | (wd[h][0][0] ^ 0x80808080u) | (wd[h][0][1] ^ 0x80808080u))) ? (1u << i1) : 0u;
         // the lane's 6-byte run: Y Co Cg Y | Co Cg
         const uint32_t lo = __funnelshift_r(nz0, nz1, sh0), hi = nz1 >> sh0;
-        f6 |= (((lo & 0xff0000ffu) ? 1u : 0u) | (((lo & 0x0000ff00u) | (hi & 0x000000ffu)) ? 2u : 0u) |
-               (((lo & 0x00ff0000u) | (hi & 0x0000ff00u)) ? 4u : 0u)) << (3 * h);
+        const unsigned ch = ((lo & 0xff0000ffu) ? 1u : 0u) | (((lo & 0x0000ff00u) | (hi & 0x000000ffu)) ? 2u : 0u) |
+                            (((lo & 0x00ff0000u) | (hi & 0x0000ff00u)) ? 4u : 0u);
+        cls[h] = __reduce_or_sync(0xffffffffu, rows | (col << 8) | (ch << 16));
       }
-      chan6 = __reduce_or_sync(0xffffffffu, f6);
     }
+    const unsigned chan6 = ((cls[0] >> 16) & 7u) | (((cls[1] >> 16) & 7u) << 3);
     const bool dc_tile = DCSKIP && chan6 == 0u;
     if (dc_tile) {
       uint4 og[2][3];
@@ -573,27 +581,46 @@ dec8_f64h_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_consta
     for (int h = 0; h < 2; ++h) {
       uint4 og[3];
       if (SSE) load_orig(tile, h, og);
+      // number of leading coefficient rows / columns that may hold non-zero indices: 2, 4 or 8
+      const unsigned rows8 = cls[h] & 0xffu, cols8 = (cls[h] >> 8) & 0xffu;
+      constexpr bool PRUNE4 = false;       // the 4-input codelets: 18 % fewer operations, but a third copy of both passes
+      const int NU = !DCSKIP ? 8 : (rows8 & 0xfcu) == 0u ? 2 : (PRUNE4 && (rows8 & 0xf0u) == 0u) ? 4 : 8;
+      const int NI = !DCSKIP ? 8 : (cols8 & 0xfcu) == 0u ? 2 : (PRUNE4 && (cols8 & 0xf0u) == 0u) ? 4 : 8;
       // ---- pass 1: dequantise + inverse DCT over u, 2 blocks per lane and channel ------
-      {
+      auto pass1 = [&](auto nu_c) {
+        constexpr int U = decltype(nu_c)::value;
         T* fw = F + i1 * H64_P + 2 * G1;
 #pragma unroll 1
         for (int c = 0; c < 3; ++c) {
           if (DCSKIP && !((chan6 >> (3 * h + c)) & 1u)) continue;      // no AC index in this channel
           T v[2][8];
 #pragma unroll
-          for (int uu = 0; uu < 8; ++uu) {
+          for (int uu = 0; uu < U; ++uu) {
             const uint32_t sv = __funnelshift_rc(wd[h][uu][0], wd[h][uu][1], sh0 + 8 * c);
             // (byte - 128) * q: int16 * int of src/2D-DCT.py:398-410 (cannot wrap for q <= 255);
             // the int -> double conversion is exact and runs off the FP64 pipe
             v[0][uu] = __int2double_rn(int(sv & 255u) * q - 128 * q);
             v[1][uu] = __int2double_rn(int(sv >> 24) * q - 128 * q);
           }
-          dct8_inv<T, EXACT>(v[0]);
-          dct8_inv<T, EXACT>(v[1]);
+          if (U == 2) {
+            dct8_inv_low2<T, EXACT>(v[0]);
+            dct8_inv_low2<T, EXACT>(v[1]);
+          } else if (U == 4) {
+            dct8_inv_low4<T, EXACT>(v[0]);
+            dct8_inv_low4<T, EXACT>(v[1]);
+          } else {
+            dct8_inv<T, EXACT>(v[0]);
+            dct8_inv<T, EXACT>(v[1]);
+          }
 #pragma unroll
           for (int yy = 0; yy < 8; ++yy)
             *reinterpret_cast<double2*>(fw + (c * 8 + yy) * H64_PP) = make_double2(v[0][yy], v[1][yy]);
         }
+      };
+      if (i1 < NI) {               // columns beyond NI are zero throughout: pass 2 does not read them
+        if (NU == 2) pass1(std::integral_constant<int, 2>());
+        else if (NU == 4) pass1(std::integral_constant<int, 4>());
+        else pass1(std::integral_constant<int, 8>());
       }
       __syncwarp();
       // ---- pass 2: inverse DCT over i, to_RGB, +128, clip, truncate ----------------------
@@ -607,26 +634,40 @@ dec8_f64h_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_consta
           yccA = __shfl_sync(0xffffffffu, lo, 8 * G2);                          // lane (i1 = 0, pair G2) holds them
           yccB = __shfl_sync(0xffffffffu, __byte_perm(lo, hi, 0x0543), 8 * G2);
         }
+        auto pass2 = [&](auto ni_c) {
+          constexpr int I = decltype(ni_c)::value;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          if (!DCSKIP || ((chan3 >> c) & 1u)) {
+          for (int c = 0; c < 3; ++c) {
+            if (!DCSKIP || ((chan3 >> c) & 1u)) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const double2 t2 = *reinterpret_cast<const double2*>(fr + c * 8 * H64_PP + i * H64_P);
-              v[c][0][i] = t2.x;
-              v[c][1][i] = t2.y;
-            }
-            dct8_inv<T, EXACT>(v[c][0]);
-            dct8_inv<T, EXACT>(v[c][1]);
-          } else {
-            const T ka = dc_chain(int((yccA >> (8 * c)) & 255u), q), kb = dc_chain(int((yccB >> (8 * c)) & 255u), q);
+              for (int i = 0; i < I; ++i) {
+                const double2 t2 = *reinterpret_cast<const double2*>(fr + c * 8 * H64_PP + i * H64_P);
+                v[c][0][i] = t2.x;
+                v[c][1][i] = t2.y;
+              }
+              if (I == 2) {
+                dct8_inv_low2<T, EXACT>(v[c][0]);
+                dct8_inv_low2<T, EXACT>(v[c][1]);
+              } else if (I == 4) {
+                dct8_inv_low4<T, EXACT>(v[c][0]);
+                dct8_inv_low4<T, EXACT>(v[c][1]);
+              } else {
+                dct8_inv<T, EXACT>(v[c][0]);
+                dct8_inv<T, EXACT>(v[c][1]);
+              }
+            } else {
+              const T ka = dc_chain(int((yccA >> (8 * c)) & 255u), q), kb = dc_chain(int((yccB >> (8 * c)) & 255u), q);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              v[c][0][i] = ka;
-              v[c][1][i] = kb;
+              for (int i = 0; i < 8; ++i) {
+                v[c][0][i] = ka;
+                v[c][1][i] = kb;
+              }
             }
           }
-        }
+        };
+        if (NI == 2) pass2(std::integral_constant<int, 2>());
+        else if (NI == 4) pass2(std::integral_constant<int, 4>());
+        else pass2(std::integral_constant<int, 8>());
         int px[2][8][3];
 #pragma unroll
         for (int b = 0; b < 2; ++b)
@@ -836,7 +877,7 @@ constexpr int PROBE_CTAS = 32;             // x 8 warps x 1 tile
 constexpr int PROBE_MIN_TILES = 4096;      // smaller jobs: not worth three extra launches
 
 struct ProbeSlot {
-  int sparse, dc_chan, ticket, choice;     // the first three are zero between launches
+  int sparse, dc_chan, low_tiles, ticket, choice;     // all but `choice` are zero between launches
 };
 
 struct ProbeArgs {
@@ -855,10 +896,11 @@ __device__ __forceinline__ uint32_t nonzero_flags(uint32_t x) {      // 0x80 in 
 // Counts, per sampled tile, the non-zero AC indices of each of its 16 blocks (all channels).
 // A block with 1..6 of them is "sparse": the kind whose samples land on exact integers.
 __global__ void __launch_bounds__(256, 1) dec8_probe_kernel(const ProbeArgs a) {
-  __shared__ int s_sparse, s_dc;            // sparse blocks; (tile, channel) pairs without AC indices
-  if (threadIdx.x == 0) {
+  __shared__ int s_sparse, s_dc, s_low;     // sparse blocks; (tile, channel) pairs without AC indices;
+  if (threadIdx.x == 0) {                   // tiles whose rows / columns 4..7 are zero throughout
     s_sparse = 0;
     s_dc = 0;
+    s_low = 0;
   }
   constexpr unsigned CH[3][3] = {{0xFF0000FFu, 0x0000FF00u, 0x00FF0000u},     // bytes of channel c in word k,
                                  {0x00FF0000u, 0xFF0000FFu, 0x0000FF00u},     // k mod 3 = 0, 1, 2
@@ -866,13 +908,14 @@ __global__ void __launch_bounds__(256, 1) dec8_probe_kernel(const ProbeArgs a) {
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int step = a.ntiles / PROBE_TILES;
-  int nsparse = 0, ndc = 0;
+  int nsparse = 0, ndc = 0, nlow = 0;
   for (int sidx = blockIdx.x * 8 + warp; sidx < PROBE_TILES; sidx += PROBE_CTAS * 8) {
     const int t = sidx * step + (sidx * 7) % step;
     const int f = t / a.per_frame, rem = t - f * a.per_frame;
     const int by = rem / a.tiles_x, tx = rem - by * a.tiles_x;
     uint32_t acc[4] = {0u, 0u, 0u, 0u};        // 16 byte-wide counters: block b in byte b & 3 of acc[b >> 2]
     uint32_t chf[3] = {0u, 0u, 0u};            // non-zero flags per channel
+    uint32_t hif = 0u;                         // non-zero flags in coefficient rows / columns 4..7
 #pragma unroll
     for (int r = 0; r < 2; ++r) {
       const int seg = lane + 32 * r, j = seg >> 3, i = seg & 7;          // subband (j, i): 16 blocks x 3 bytes
@@ -891,6 +934,7 @@ __global__ void __launch_bounds__(256, 1) dec8_probe_kernel(const ProbeArgs a) {
           acc[g] += c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);          // <= 3 per segment, 189 per tile: no carry
 #pragma unroll
           for (int c = 0; c < 3; ++c) chf[c] |= (f0 & CH[0][c]) | (f1 & CH[1][c]) | (f2 & CH[2][c]);
+          if (j >= 4 || i >= 4) hif |= f0 | f1 | f2;
         }
       }
     }
@@ -900,23 +944,28 @@ __global__ void __launch_bounds__(256, 1) dec8_probe_kernel(const ProbeArgs a) {
     nsparse += __popc(__ballot_sync(0xffffffffu, mine >= 1u && mine <= 6u));
 #pragma unroll
     for (int c = 0; c < 3; ++c) ndc += !__any_sync(0xffffffffu, chf[c] != 0u);
+    nlow += !__any_sync(0xffffffffu, hif != 0u);
   }
   if (lane == 0) {
     atomicAdd(&s_sparse, nsparse);
     atomicAdd(&s_dc, ndc);
+    atomicAdd(&s_low, nlow);
   }
   __syncthreads();
   if (threadIdx.x == 0) {
     ProbeSlot* sl = a.slot;
     atomicAdd(&sl->sparse, s_sparse);
     atomicAdd(&sl->dc_chan, s_dc);
+    atomicAdd(&sl->low_tiles, s_low);
     __threadfence();
     if (atomicAdd(&sl->ticket, 1) == PROBE_CTAS - 1) {      // last CTA: decide, and leave the slot clean
       __threadfence();
-      const int sparse = atomicExch(&sl->sparse, 0), dc = atomicExch(&sl->dc_chan, 0);
+      const int sparse = atomicExch(&sl->sparse, 0), dc = atomicExch(&sl->dc_chan, 0), low = atomicExch(&sl->low_tiles, 0);
       int kind = DEC_EXACT;
       if (50 * sparse <= PROBE_TILES * 16) kind = DEC_TWO_TIER;         // <= 2 % sparse blocks
-      else if (8 * dc > 3 * PROBE_TILES) kind = DEC_EXACT_DCSKIP;       // > 1/8 of the (tile, channel) pairs without AC
+      else if (8 * dc > 3 * PROBE_TILES ||                              // > 1/8 of the (tile, channel) pairs without AC,
+               4 * low > PROBE_TILES)                                   // or > 1/4 of the tiles low-frequency only
+        kind = DEC_EXACT_DCSKIP;
       sl->choice = kind;
       sl->ticket = 0;
     }
