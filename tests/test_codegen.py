@@ -17,7 +17,7 @@ def _run_emitted(src: str, x, dtype):
     import re
     import numpy as np
     env = {}
-    out = [None] * 8
+    out = [None] * len(x)
 
     def val(tok):
         tok = tok.strip()
@@ -63,22 +63,22 @@ def _run_emitted(src: str, x, dtype):
 
 
 def test_pruned_inverse_codelets_are_bit_exact():
-    """dct8_inv_low2 / _low4 (inputs known to be zero dropped) against the real scipy: bitwise,
-    float32 and float64 (the lazy output scale of dct8_inv is 2^-2)."""
+    """dct8_inv_low2 / _low4, dct16_inv_low2 / _low4 (inputs known to be zero dropped) against the real scipy:
+    bitwise, float32 and float64 (the lazy output scale of dct8_inv is 2^-2, of dct16_inv 1)."""
     import numpy as np
     import scipy.fftpack as sf
     sys.path.insert(0, ROOT)
     from vcf_b200.codegen import gen_cuda as G
     rng = np.random.default_rng(11)
-    for nin in (2, 4):
-        src = G.emit_pruned_codelet(8, True, nin)
+    for n, nin, scale in ((8, 2, 0.25), (8, 4, 0.25), (16, 2, 1.0), (16, 4, 1.0)):
+        src = G.emit_pruned_codelet(n, True, nin)
         for dtype in (np.float64, np.float32):
             for _ in range(400):
-                x = np.zeros(8, dtype=dtype)
+                x = np.zeros(n, dtype=dtype)
                 x[:nin] = rng.integers(-32768, 32768, size=nin)
                 if rng.random() < 0.3:
                     x[rng.integers(0, nin)] = 0
-                got = np.array(_run_emitted(src, x, dtype), dtype=dtype) * dtype(0.25)
+                got = np.array(_run_emitted(src, x, dtype), dtype=dtype) * dtype(scale)
                 want = sf.idct(x, norm="ortho")
                 assert want.dtype == dtype
                 assert np.array_equal(got, want), (nin, dtype, x, got, want)

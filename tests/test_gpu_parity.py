@@ -328,6 +328,21 @@ def test_fast16_decode_path_exact(q, color, torch_cuda):
         assert s["sumdiff"] == int((frames.astype(np.int64) - ref.astype(np.int64)).sum())
         got2 = dec.decode(t.from_numpy(idx).cuda(), (H, W))
         assert np.array_equal(got2.cpu().numpy(), ref)
+    # index arrays whose non-zero extent changes from one group of 8 blocks to the next: the pruned
+    # codelet (dct16_inv_low4), its column skip, and the switch back to the full one
+    H, W = 64, 1024
+    ny, nx = H // 16, W // 16
+    kk = np.zeros((ny, nx, 16, 16, 3), dtype=np.int64)
+    kk[:, :, 0, 0, :] = rng.integers(-40, 41, size=(ny, nx, 3))
+    for by in range(ny):
+        for g0 in range(0, nx, 8):
+            nu, ni = int(rng.choice([1, 2, 4, 5, 16])), int(rng.choice([1, 2, 4, 5, 16]))
+            kk[by, g0:g0 + 8, :nu, :ni, :] = rng.integers(-9, 10, size=(8, nu, ni, 3))
+    idx = (kk.transpose(2, 0, 3, 1, 4).reshape(H, W, 3) + 128).astype(np.uint8)
+    ref = O.decode_array(idx, (H, W, 3), 16, q, color=color)
+    got = _codec(block_size=16, q=q, color=color, fp64=True).decode(t.from_numpy(idx).cuda(), (H, W))
+    assert _lib.last_kernel() == "dec16_fast"
+    assert np.array_equal(got.cpu().numpy(), ref), ("extent mix", q, color, int((got.cpu().numpy() != ref).sum()))
     # vertical padding takes the general kernel
     img = O.synthetic_frame(40, 256, 3, "natural")
     k = O.encode_array(img, 16, q, color=color)

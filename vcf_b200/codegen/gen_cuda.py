@@ -186,7 +186,7 @@ def emit_pruned_codelet(n: int, inverse: bool, nin: int) -> str:
 
 
 # pruned variants emitted: (n, inverse, number of leading inputs that may be non-zero)
-PRUNED = ((8, True, 2), (8, True, 4))
+PRUNED = ((8, True, 2), (8, True, 4), (16, True, 2), (16, True, 4))
 
 
 def generate() -> str:

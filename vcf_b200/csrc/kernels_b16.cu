@@ -299,6 +299,7 @@ int launch_enc16(const CUtensorMap& in_map, const CUtensorMap& out_map, const En
 constexpr int D16_PITCH = 8 * 16 + 2;                // doubles per (c, y) row: 8 blocks x 16 columns, + 16 bytes
 constexpr int D16_F_BYTES = 3 * 16 * D16_PITCH * 8;  // 49920
 constexpr int DEC16_SMEM = NST16 * T16_BYTES + D16_F_BYTES + 64;
+constexpr int PRUNE16 = 4;                           // rows / columns kept by the pruned codelet (dct16_inv_low4)
 
 struct Dec16Args {
   int ntiles, tiles_x, ny, top;
@@ -394,6 +395,23 @@ dec16_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__
 
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
+      // Extent of the non-zero indices of this half-tile: when the coefficient rows (columns) from
+      // PRUNE16 on are zero in all 8 blocks, pass 1 (pass 2) runs the pruned codelet -- the same
+      // operations minus those on exact zeros -- and the threads of all-zero columns skip pass 1.
+      bool hi_row = false, hi_col = false;
+      {
+        uint32_t lowu = 0, highu = 0;              // index bytes are 0x80 for a zero index
+#pragma unroll
+        for (int j = 0; j < 12; ++j) {
+          const uint32_t t = kw[h][j] ^ 0x80808080u;
+          if (j < (PRUNE16 * 3) / 4) lowu |= t;                                        // rows 0 .. PRUNE16-1
+          else highu |= t;
+        }
+        hi_row = highu != 0u;
+        hi_col = i1 >= PRUNE16 && (lowu | highu) != 0u;
+      }
+      const bool full_u = __syncthreads_or(hi_row) != 0;
+      const bool full_i = __syncthreads_or(hi_col) != 0;
       uint4 og[3];
       if (SSE) {
         int f, by, tx;
@@ -405,7 +423,7 @@ dec16_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__
         og[2] = __ldg(p + 2);
       }
       // ---- pass 1 -------------------------------------------------------------------------
-      {
+      if (full_i || i1 < PRUNE16) {
         double* fw = F + b1 * 16 + i1;
 #pragma unroll 1
         for (int c = 0; c < 3; ++c) {
@@ -422,7 +440,8 @@ dec16_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__
             v[4 * g + 2] = __int2double_rn(k2 * q - 128 * q);
             v[4 * g + 3] = __int2double_rn(k3 * q - 128 * q);
           }
-          dct16_inv<double, true>(v);
+          if (full_u) dct16_inv<double, true>(v);
+          else dct16_inv_low4<double, true>(v);
 #pragma unroll
           for (int yy = 0; yy < 16; ++yy) fw[(c * 16 + yy) * D16_PITCH] = v[yy];
         }
@@ -441,15 +460,28 @@ dec16_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__
       {
         const double* fr = F + y2 * D16_PITCH + b2 * 16;
         double v[3][16];
+        if (full_i) {
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
+          for (int c = 0; c < 3; ++c) {
 #pragma unroll
-          for (int m = 0; m < 8; ++m) {
-            const double2 t2 = *reinterpret_cast<const double2*>(fr + c * 16 * D16_PITCH + 2 * m);
-            v[c][2 * m] = t2.x;
-            v[c][2 * m + 1] = t2.y;
+            for (int m = 0; m < 8; ++m) {
+              const double2 t2 = *reinterpret_cast<const double2*>(fr + c * 16 * D16_PITCH + 2 * m);
+              v[c][2 * m] = t2.x;
+              v[c][2 * m + 1] = t2.y;
+            }
+            dct16_inv<double, true>(v[c]);
           }
-          dct16_inv<double, true>(v[c]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+#pragma unroll
+            for (int m = 0; m < PRUNE16 / 2; ++m) {
+              const double2 t2 = *reinterpret_cast<const double2*>(fr + c * 16 * D16_PITCH + 2 * m);
+              v[c][2 * m] = t2.x;
+              v[c][2 * m + 1] = t2.y;
+            }
+            dct16_inv_low4<double, true>(v[c]);
+          }
         }
         int px[16][3];
 #pragma unroll
