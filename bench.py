@@ -493,6 +493,32 @@ def run_ours(a):
             line["entropy_stage"] = {"codec": "zlib level 6 on one frame of indices (q=%d), 1 host core" % q_ent,
                                      "mpixel_s": H * W / 1e6 / dt, "bits_per_pixel": 8.0 * len(comp) / (H * W),
                                      "note": "not part of `value` or `e2e`; the reference's containers (TIFF/PNG/npz) wrap the same deflate"}
+            # row F4: the same stage on the GPU (vcfb_deflate_dev), on a batch of index planes resident in HBM
+            from vcf_b200 import _lib as _L
+            from vcf_b200.entropy import deflate_raw_dev
+            nf = max(1, min(n, 16))
+            kb = enc[q_ent].encode(x[:nf]).reshape(-1)
+            dst, nb = deflate_raw_dev(kb)           # warm-up, and the stream that is checked
+            one, nb1 = deflate_raw_dev(kb[: k.size])
+            torch.cuda.synchronize()
+            ok = zlib.decompress(one[: int(nb1.item())].cpu().numpy().tobytes(), -15) == k.tobytes()
+            L_ = _L.lib()
+            ws = torch.empty(L_.vcfb_deflate_workspace(kb.numel()), dtype=torch.uint8, device=kb.device)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 10
+            e0.record()
+            for _ in range(reps):
+                _L.check(L_.vcfb_deflate_dev(kb.data_ptr(), kb.numel(), dst.data_ptr(), dst.numel(), nb.data_ptr(),
+                                             ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream))
+            e1.record()
+            torch.cuda.synchronize()
+            gms = e0.elapsed_time(e1) / reps
+            line["entropy_stage"]["gpu_deflate"] = {
+                "api": "vcfb_deflate_dev (run-length parse + dynamic Huffman, 3 kernels), %d frames of indices per call, in HBM" % nf,
+                "ms_per_call": gms, "mpixel_s": nf * H * W / 1e6 / (gms / 1e3), "input_GB_s": kb.numel() / 1e9 / (gms / 1e3),
+                "bits_per_pixel": 8.0 * int(nb.item()) / (nf * H * W),
+                "bits_per_pixel_one_frame": 8.0 * int(nb1.item()) / (H * W),
+                "zlib_reads_it_back": bool(ok)}
         except Exception as exc:      # never let the side measurement break the bench line
             line["entropy_stage"] = {"error": str(exc)}
     print(json.dumps(line))

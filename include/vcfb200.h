@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define VCFB_VERSION 110 /* 0.1.1: + vcfb_launch_count, vcfb_gray_dev, vcfb_block_match_dev, vcfb_block_match_tss_dev */
+#define VCFB_VERSION 120 /* 0.2.0: + vcfb_deflate_dev, vcfb_deflate_bound, vcfb_deflate_workspace (0.1.1: vcfb_launch_count, motion estimation) */
 
 /* error codes */
 #define VCFB_OK 0
@@ -161,6 +161,25 @@ int vcfb_block_match_dev(const uint8_t* ref, const uint8_t* cur, int n_frames, i
                          int16_t* mv_out, void* cuda_stream);
 int vcfb_block_match_tss_dev(const uint8_t* ref, const uint8_t* cur, int n_frames, int H, int W, int bs, int sr,
                              int16_t* mv_out, void* cuda_stream);
+
+/* Entropy front-end: raw deflate (RFC 1951) of a byte array -- the zlib call
+ * underneath the reference's entropy stage for the uint8 index planes (np.savez_compressed in
+ * src/z_lib.py:19-23; tifffile's zlib codec in src/TIFF.py:23-31).  Run-length parse (distance-1
+ * matches, zlib's Z_RLE strategy) + one dynamic Huffman block per segment of 132-528 KB, stored
+ * blocks where those are smaller.  The stream is complete (last block has BFINAL = 1) and any
+ * inflate implementation reads it: zlib.decompress(stream, -15); prefix 78 9C and append the
+ * big-endian Adler-32 for a zlib stream; wrap in a zip member with its CRC-32 for .npz.
+ * It is NOT byte-identical with zlib's output -- the property kept is that the reference's decoder
+ * (np.load / tifffile.imread / zlib.decompress) returns the same array.
+ * src        n_bytes bytes, device, 8-byte aligned
+ * dst        device, dst_capacity >= vcfb_deflate_bound(n_bytes)
+ * out_bytes  one uint64 on the device: length of the stream in dst
+ * workspace  device, 16-byte aligned, >= vcfb_deflate_workspace(n_bytes) bytes (about n_bytes)
+ * Asynchronous on cuda_stream; three kernels (segments, scan, gather). */
+size_t vcfb_deflate_bound(size_t n_bytes);
+size_t vcfb_deflate_workspace(size_t n_bytes);
+int vcfb_deflate_dev(const uint8_t* src, size_t n_bytes, uint8_t* dst, size_t dst_capacity,
+                     uint64_t* out_bytes, void* workspace, size_t workspace_bytes, void* cuda_stream);
 
 /* Host-buffer convenience layer (what a numpy caller binds).  A context owns one
  * CUDA stream plus pinned and device staging buffers that grow on demand. */

@@ -1,0 +1,94 @@
+// Host emulation of deflate_segments_kernel / deflate_scan_kernel / deflate_gather_kernel
+// (vcf_b200/csrc/kernels_deflate.cu): the same __host__ __device__ code from
+// vcf_b200/csrc/deflate_core.cuh, compiled with g++, the CTA's phases run one "thread" after the
+// other.  TEST INFRASTRUCTURE ONLY: built and loaded by tests/test_deflate_core.py so that the
+// parsing / Huffman / header / bit-packing logic is checked against zlib's decoder on machines
+// without a GPU.  Nothing in vcf_b200/ uses it.
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../vcf_b200/csrc/deflate_core.cuh"
+
+using namespace vcfb;
+
+extern "C" long long dfl_emul(const uint8_t* src, long long n, int piece, int NT, uint8_t* dst, long long cap,
+                              long long* n_stored_segments) {
+  const long long seg_bytes = (long long)NT * piece;
+  const long long nsegs = (n + seg_bytes - 1) / seg_bytes;
+  const long long stride = (dfl::stored_size(seg_bytes) + 15) / 16 * 16 + 16;
+  std::vector<uint8_t> region(stride);
+  long long pos = 0, stored_count = 0;
+  for (long long seg = 0; seg < nsegs; ++seg) {
+    uint32_t hist[288];
+    dfl::Codes codes;
+    dfl::Header hdr;
+    dfl::BuildScratch scratch;
+    std::vector<uint32_t> off(NT);
+    const long long s0 = seg * seg_bytes;
+    const long long nseg = std::min(n - s0, seg_bytes);
+    auto S = [&](int tid) { return std::min(n, s0 + (long long)tid * piece); };
+    auto E = [&](int tid) { return std::min(n, S(tid) + piece); };
+    for (int i = 0; i < 288; ++i) hist[i] = 0;
+    hist[dfl::EOB] = 1;
+    for (int tid = 0; tid < NT; ++tid) {
+      dfl::CountVisitor cv;
+      cv.init(hist);
+      dfl::parse_piece(src, S(tid), E(tid), cv);
+      cv.flush();
+    }
+    for (int i = 0; i < dfl::NLIT; ++i)
+      if (hist[i]) scratch.sorted[dfl::rank_of(hist, dfl::NLIT, i)] = uint16_t(i);
+    dfl::segment_build(hist, scratch, codes, hdr);
+    for (int tid = 0; tid < NT; ++tid) {
+      dfl::SizeVisitor sv;
+      sv.len = codes.len;
+      sv.bits = 0;
+      dfl::parse_piece(src, S(tid), E(tid), sv);
+      off[tid] = sv.bits;
+    }
+    long long acc = hdr.bits;
+    for (int t = 0; t < NT; ++t) {
+      const uint32_t b = off[t];
+      off[t] = uint32_t(acc);
+      acc += b;
+    }
+    const long long dyn = dfl::dynamic_size(hdr, codes, acc - hdr.bits);
+    const long long st = dfl::stored_size(nseg);
+    const bool stored = dyn >= st;
+    const long long total = stored ? st : dyn;
+    std::fill(region.begin(), region.end(), 0xAA);     // the kernel's scratch is not zero either
+    if (stored) {
+      ++stored_count;
+      for (int tid = 0; tid < NT; ++tid) dfl::stored_copy(src + s0, nseg, S(tid) - s0, E(tid) - s0, region.data());
+    } else {
+      memset(region.data(), 0, size_t((total + 15) / 16 * 16));
+      // threads in reverse order: the result must not depend on who writes a shared word first
+      for (int tid = NT - 1; tid >= 0; --tid) {
+        dfl::BitWriter bw;
+        bw.init(reinterpret_cast<uint32_t*>(region.data()), tid == 0 ? 0 : (long long)off[tid]);
+        if (tid == 0) dfl::header_emit(hdr, bw);
+        dfl::EmitVisitor ev;
+        ev.c = &codes;
+        ev.bw = &bw;
+        dfl::parse_piece(src, S(tid), E(tid), ev);
+        if (tid == 0 && bw.bitpos() != (NT > 1 ? (long long)off[1] : bw.bitpos()) && S(1) < E(1)) return -2;
+        if (tid == NT - 1) {
+          dfl::segment_close(codes, bw);
+          if (bw.bitpos() != total * 8) return -3;
+        }
+        bw.finish();
+      }
+    }
+    if (pos + total + 2 > cap) return -1;
+    memcpy(dst + pos, region.data(), size_t(total));
+    pos += total;
+  }
+  if (pos + 2 > cap) return -1;
+  dst[pos++] = 0x03;
+  dst[pos++] = 0x00;
+  if (n_stored_segments) *n_stored_segments = stored_count;
+  return pos;
+}

@@ -8,4 +8,4 @@ from .codec import (  # noqa: F401
 )
 from ._lib import VcfbError  # noqa: F401
 
-__version__ = "0.1.1"
+__version__ = "0.2.0"

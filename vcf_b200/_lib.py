@@ -75,6 +75,13 @@ def lib():
     L.vcfb_block_match_dev.restype = i
     L.vcfb_block_match_tss_dev.argtypes = [vp, vp, i, i, i, i, i, vp, vp]
     L.vcfb_block_match_tss_dev.restype = i
+    sz = C.c_size_t
+    L.vcfb_deflate_bound.argtypes = [sz]
+    L.vcfb_deflate_bound.restype = sz
+    L.vcfb_deflate_workspace.argtypes = [sz]
+    L.vcfb_deflate_workspace.restype = sz
+    L.vcfb_deflate_dev.argtypes = [vp, sz, vp, sz, vp, vp, sz, vp]
+    L.vcfb_deflate_dev.restype = i
     _lib = L
     return L
 

@@ -1,0 +1,242 @@
+// Entropy front-end: raw deflate (RFC 1951) of a byte array on the GPU.
+//
+// Replaces the zlib call underneath the reference's entropy stage for the uint8 index planes of
+// the transform path (np.savez_compressed, src/z_lib.py:19-23; the zlib codec of tifffile,
+// src/TIFF.py:23-31).  The output is an ordinary deflate stream: zlib.decompress / np.load /
+// tifffile read it.  It is not byte-identical with zlib's output (no two deflate encoders are);
+// the drop-in property is "the reference's decoder returns the same bytes".
+//
+//   deflate_segments_kernel  one CTA per segment of NT pieces.  Phase 1: every thread parses its
+//       piece (run-length parse, deflate_core.cuh) into a shared histogram.  Phase 2: rank sort
+//       of the used symbols by all threads, Huffman code + block header by thread 0.  Phase 3:
+//       every thread sizes its piece under the code; exclusive scan -> bit offsets; the segment
+//       falls back to stored blocks when those are smaller.  Phase 4: the CTA zeroes exactly the
+//       bytes the block takes, every thread writes its tokens at its bit offset (first and last
+//       word with atomicOr, the rest with plain stores).
+//   deflate_scan_kernel      exclusive scan of the segment sizes, total size, closing block.
+//   deflate_gather_kernel    copies every segment's bytes to its place in the output stream.
+#include "common.cuh"
+#include "deflate_core.cuh"
+
+namespace vcfb {
+namespace {
+
+constexpr int NT = 512;
+
+struct Plan {
+  int piece;              // bytes per thread
+  long long seg_bytes;    // bytes per segment = NT * piece
+  long long nseg;
+  long long stride;       // bytes of scratch per segment
+  long long sizes_off, offs_off, regions_off, total;   // workspace layout
+  long long bound;        // largest possible stream
+};
+
+Plan make_plan(unsigned long long n) {
+  Plan p;
+  // multiples of the longest match (258): a piece that lies inside a long run becomes matches of
+  // length 258 (symbol 285, no extra bits), as in a sequential parse
+  p.piece = n >= (64ull << 20) ? 4 * dfl::MAX_MATCH : n >= (4ull << 20) ? 2 * dfl::MAX_MATCH : dfl::MAX_MATCH;
+  p.seg_bytes = (long long)NT * p.piece;
+  p.nseg = (long long)((n + p.seg_bytes - 1) / p.seg_bytes);
+  p.stride = (dfl::stored_size(p.seg_bytes) + 15) / 16 * 16 + 16;
+  p.sizes_off = 0;
+  p.offs_off = (p.nseg * 4 + 15) / 16 * 16;
+  p.regions_off = p.offs_off + (p.nseg * 8 + 15) / 16 * 16;
+  p.total = p.regions_off + p.nseg * p.stride + 16;
+  p.bound = (long long)n + 5 * p.nseg * ((p.seg_bytes + dfl::STORED_MAX - 1) / dfl::STORED_MAX) + 2;
+  return p;
+}
+
+struct SegShared {
+  uint32_t hist[288];
+  dfl::Codes codes;
+  dfl::Header hdr;
+  dfl::BuildScratch scratch;
+  uint32_t off[NT];
+  long long total_bytes;
+  int stored;
+};
+
+__global__ void __launch_bounds__(NT)
+deflate_segments_kernel(const uint8_t* __restrict__ src, long long n, int piece, uint8_t* __restrict__ regions,
+                        long long stride, uint32_t* __restrict__ seg_size) {
+  __shared__ SegShared sh;
+  const int tid = threadIdx.x;
+  const long long seg = blockIdx.x;
+  const long long seg_bytes = (long long)NT * piece;
+  const long long s0 = seg * seg_bytes;
+  const long long nseg = min(n - s0, seg_bytes);
+  const long long s = min(n, s0 + (long long)tid * piece);
+  const long long e = min(n, s + piece);
+  uint8_t* out = regions + seg * stride;
+
+  for (int i = tid; i < 288; i += NT) sh.hist[i] = 0;
+  __syncthreads();
+  if (tid == 0) sh.hist[dfl::EOB] = 1;
+
+  // phase 1: symbol frequencies
+  {
+    dfl::CountVisitor cv;
+    cv.init(sh.hist);
+    dfl::parse_piece(src, s, e, cv);
+    cv.flush();
+  }
+  __syncthreads();
+
+  // phase 2: code construction
+  for (int i = tid; i < dfl::NLIT; i += NT)
+    if (sh.hist[i]) sh.scratch.sorted[dfl::rank_of(sh.hist, dfl::NLIT, i)] = uint16_t(i);
+  __syncthreads();
+  if (tid == 0) dfl::segment_build(sh.hist, sh.scratch, sh.codes, sh.hdr);
+  __syncthreads();
+
+  // phase 3: sizes and bit offsets
+  {
+    dfl::SizeVisitor sv;
+    sv.len = sh.codes.len;
+    sv.bits = 0;
+    dfl::parse_piece(src, s, e, sv);
+    sh.off[tid] = sv.bits;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    long long acc = sh.hdr.bits;
+    for (int t = 0; t < NT; ++t) {
+      const uint32_t b = sh.off[t];
+      sh.off[t] = uint32_t(acc);
+      acc += b;
+    }
+    const long long dyn = dfl::dynamic_size(sh.hdr, sh.codes, acc - sh.hdr.bits);
+    const long long st = dfl::stored_size(nseg);
+    sh.stored = dyn >= st;
+    sh.total_bytes = sh.stored ? st : dyn;
+    seg_size[seg] = uint32_t(sh.total_bytes);
+  }
+  __syncthreads();
+
+  // phase 4: output
+  if (sh.stored) {
+    dfl::stored_copy(src + s0, nseg, s - s0, e - s0, out);
+    return;
+  }
+  {
+    const int n16 = int((sh.total_bytes + 15) / 16);
+    uint4* o4 = reinterpret_cast<uint4*>(out);
+    for (int i = tid; i < n16; i += NT) o4[i] = make_uint4(0, 0, 0, 0);
+  }
+  __syncthreads();
+  {
+    dfl::BitWriter bw;
+    bw.init(reinterpret_cast<uint32_t*>(out), tid == 0 ? 0 : (long long)sh.off[tid]);
+    if (tid == 0) dfl::header_emit(sh.hdr, bw);
+    dfl::EmitVisitor ev;
+    ev.c = &sh.codes;
+    ev.bw = &bw;
+    dfl::parse_piece(src, s, e, ev);
+    if (tid == NT - 1) dfl::segment_close(sh.codes, bw);
+    bw.finish();
+  }
+}
+
+// one CTA: exclusive scan of the segment sizes; the stream is closed with an empty fixed-Huffman
+// block with BFINAL = 1 (bits 1, 01, 0000000 -> bytes 03 00)
+__global__ void __launch_bounds__(NT)
+deflate_scan_kernel(const uint32_t* __restrict__ seg_size, long long nseg, unsigned long long* __restrict__ seg_off,
+                    uint8_t* __restrict__ dst, unsigned long long* __restrict__ out_bytes) {
+  __shared__ unsigned long long part[NT];
+  const int tid = threadIdx.x;
+  const long long per = (nseg + NT - 1) / NT;
+  const long long a = min(nseg, tid * per), b = min(nseg, a + per);
+  unsigned long long sum = 0;
+  for (long long i = a; i < b; ++i) sum += seg_size[i];
+  part[tid] = sum;
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long acc = 0;
+    for (int t = 0; t < NT; ++t) {
+      const unsigned long long v = part[t];
+      part[t] = acc;
+      acc += v;
+    }
+    dst[acc] = 0x03;
+    dst[acc + 1] = 0x00;
+    *out_bytes = acc + 2;
+  }
+  __syncthreads();
+  unsigned long long acc = part[tid];
+  for (long long i = a; i < b; ++i) {
+    seg_off[i] = acc;
+    acc += seg_size[i];
+  }
+}
+
+__global__ void __launch_bounds__(NT)
+deflate_gather_kernel(const uint8_t* __restrict__ regions, long long stride, const uint32_t* __restrict__ seg_size,
+                      const unsigned long long* __restrict__ seg_off, uint8_t* __restrict__ dst) {
+  const long long seg = blockIdx.x;
+  const uint8_t* in = regions + seg * stride;
+  uint8_t* out = dst + seg_off[seg];
+  const unsigned nb = seg_size[seg];
+  // bytes up to the first 16-byte boundary of the destination, then 16-byte stores fed by byte-aligned
+  // 4-byte reads would need a shifter; the compressed stream is small, so plain words where both sides
+  // are 4-byte aligned and bytes otherwise
+  if (((reinterpret_cast<uintptr_t>(out) & 3) == 0)) {
+    const unsigned nw = nb / 4;
+    const uint32_t* in4 = reinterpret_cast<const uint32_t*>(in);
+    uint32_t* out4 = reinterpret_cast<uint32_t*>(out);
+    for (unsigned i = threadIdx.x; i < nw; i += NT) out4[i] = in4[i];
+    for (unsigned i = nw * 4 + threadIdx.x; i < nb; i += NT) out[i] = in[i];
+  } else {
+    for (unsigned i = threadIdx.x; i < nb; i += NT) out[i] = in[i];
+  }
+}
+
+}  // namespace
+}  // namespace vcfb
+
+using namespace vcfb;
+
+extern "C" {
+
+size_t vcfb_deflate_bound(size_t n_bytes) { return size_t(make_plan(n_bytes).bound); }
+
+size_t vcfb_deflate_workspace(size_t n_bytes) { return size_t(make_plan(n_bytes).total); }
+
+int vcfb_deflate_dev(const uint8_t* src, size_t n_bytes, uint8_t* dst, size_t dst_capacity,
+                     uint64_t* out_bytes, void* workspace, size_t workspace_bytes, void* cuda_stream) {
+  if (!dst || !out_bytes) { set_error("output pointer is NULL"); return VCFB_E_ARG; }
+  if (n_bytes && !src) { set_error("input pointer is NULL"); return VCFB_E_ARG; }
+  if (n_bytes >= (1ull << 40)) { set_error("input too large"); return VCFB_E_ARG; }
+  if (reinterpret_cast<uintptr_t>(src) & 7) { set_error("vcfb_deflate_dev: src must be 8-byte aligned"); return VCFB_E_ARG; }
+  const Plan p = make_plan(n_bytes);
+  if (dst_capacity < size_t(p.bound)) { set_error("vcfb_deflate_dev: dst_capacity is below vcfb_deflate_bound()"); return VCFB_E_ARG; }
+  if (workspace_bytes < size_t(p.total) || (!workspace && p.total)) { set_error("vcfb_deflate_dev: workspace is below vcfb_deflate_workspace()"); return VCFB_E_ARG; }
+  if (reinterpret_cast<uintptr_t>(workspace) & 15) { set_error("vcfb_deflate_dev: workspace must be 16-byte aligned"); return VCFB_E_ARG; }
+  if (p.nseg > 0x7fffffffLL) { set_error("input too large"); return VCFB_E_ARG; }
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(cuda_stream);
+  uint8_t* ws = static_cast<uint8_t*>(workspace);
+  uint32_t* seg_size = reinterpret_cast<uint32_t*>(ws + p.sizes_off);
+  unsigned long long* seg_off = reinterpret_cast<unsigned long long*>(ws + p.offs_off);
+  uint8_t* regions = ws + p.regions_off;
+  cudaError_t e;
+  if (p.nseg) {
+    note_kernel("deflate_segments");
+    deflate_segments_kernel<<<unsigned(p.nseg), NT, 0, s>>>(src, (long long)n_bytes, p.piece, regions, p.stride, seg_size);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "deflate_segments_kernel launch");
+  }
+  note_kernel("deflate_scan");
+  deflate_scan_kernel<<<1, NT, 0, s>>>(seg_size, p.nseg, seg_off, dst, reinterpret_cast<unsigned long long*>(out_bytes));
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "deflate_scan_kernel launch");
+  if (p.nseg) {
+    note_kernel("deflate_gather");
+    deflate_gather_kernel<<<unsigned(p.nseg), NT, 0, s>>>(regions, p.stride, seg_size, seg_off, dst);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "deflate_gather_kernel launch");
+  }
+  return VCFB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,138 @@
+"""Entropy front-end on the GPU: deflate streams the reference's own
+decoders read.
+
+The reference compresses the uint8 index planes of the transform path with zlib on the host --
+``np.savez_compressed`` in /root/reference/src/z_lib.py:19-23, tifffile's zlib codec in
+src/TIFF.py:23-31 -- and once the transform runs on the GPU that call is the slowest stage left
+(``entropy_stage`` in bench.py).  ``vcfb_deflate_dev`` (csrc/kernels_deflate.cu) produces a raw
+deflate stream on the device; this module wraps it in the containers the reference uses:
+
+* ``deflate_raw(x)``          raw RFC 1951 stream        -> ``zlib.decompress(s, -15)``
+* ``zlib_compress(x)``        RFC 1950 (78 9C ... adler) -> ``zlib.decompress(s)``
+* ``savez_compressed(f, a=x)`` .npz (zip, method 8)      -> ``np.load(f)['a']`` as in src/z_lib.py:25-29
+
+The streams are not byte-identical with zlib's (a different, run-length parse); what is kept is
+that the reference's decoder returns the same array.  Checksums (Adler-32 / CRC-32) are taken
+with the host's zlib over the host copy of the array.  There is no CPU fallback for the
+compression itself.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import io
+import struct
+import zlib
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _as_device_bytes(x):
+    """uint8 view (1-D, contiguous, 8-byte aligned) of a numpy array or torch tensor on the GPU."""
+    import torch
+    if not torch.cuda.is_available():
+        raise _lib.VcfbError("no CUDA device: vcf_b200 has no CPU fallback")
+    if not _is_torch(x):
+        x = torch.from_numpy(np.ascontiguousarray(x).reshape(-1).view(np.uint8))
+    if not x.is_cuda:
+        x = x.cuda(non_blocking=True)
+    x = x.contiguous().reshape(-1).view(torch.uint8)
+    if x.data_ptr() % 8:
+        x = x.clone()
+    return x
+
+
+def deflate_raw_dev(x):
+    """Asynchronous on torch's current stream: returns ``(stream, n)`` -- a uint8 CUDA tensor of
+    capacity ``vcfb_deflate_bound`` and a one-element int64 CUDA tensor with the stream length."""
+    import torch
+    x = _as_device_bytes(x)
+    L = _lib.lib()
+    n = x.numel()
+    dst = torch.empty(L.vcfb_deflate_bound(n), dtype=torch.uint8, device=x.device)
+    ws = torch.empty(L.vcfb_deflate_workspace(n), dtype=torch.uint8, device=x.device)
+    out_n = torch.zeros(1, dtype=torch.int64, device=x.device)
+    with torch.cuda.device(x.device):
+        check(L.vcfb_deflate_dev(x.data_ptr(), n, dst.data_ptr(), dst.numel(), out_n.data_ptr(), ws.data_ptr(),
+                                 ws.numel(), torch.cuda.current_stream().cuda_stream))
+    return dst, out_n
+
+
+def deflate_raw(x) -> bytes:
+    """Raw deflate stream of the bytes of ``x`` (numpy array or torch tensor)."""
+    dst, out_n = deflate_raw_dev(x)
+    n = int(out_n.item())
+    return dst[:n].cpu().numpy().tobytes()
+
+
+def _host_bytes(x) -> memoryview:
+    if _is_torch(x):
+        x = x.detach().cpu().numpy()
+    return memoryview(np.ascontiguousarray(x).reshape(-1).view(np.uint8))
+
+
+def zlib_compress(x) -> bytes:
+    """zlib-format stream (what ``zlib.compress`` returns): ``zlib.decompress`` reads it."""
+    raw = deflate_raw(x)
+    return b"\x78\x9c" + raw + struct.pack(">I", zlib.adler32(_host_bytes(x)) & 0xFFFFFFFF)
+
+
+def _npy_header(a: np.ndarray) -> bytes:
+    fh = io.BytesIO()
+    np.lib.format.write_array_header_1_0(fh, np.lib.format.header_data_from_array_1_0(a))
+    return fh.getvalue()
+
+
+def _stored_block(data: bytes) -> bytes:
+    """Non-final stored deflate block(s) holding ``data`` (RFC 1951 3.2.4)."""
+    out = []
+    for i in range(0, len(data), 65535):
+        part = data[i:i + 65535]
+        out.append(b"\x00" + struct.pack("<HH", len(part), len(part) ^ 0xFFFF) + part)
+    return b"".join(out)
+
+
+def savez_compressed(file, **arrays) -> None:
+    """``np.savez_compressed(file, **arrays)`` with the deflate streams produced on the GPU.
+    ``file``: path or binary file object.  ``np.load`` reads the result (src/z_lib.py:25-29)."""
+    own = isinstance(file, (str, bytes)) or hasattr(file, "__fspath__")
+    fh = open(file, "wb") if own else file
+    try:
+        start = fh.tell()
+        central = []
+        for name, arr in arrays.items():
+            if _is_torch(arr):
+                host = arr.detach().cpu().numpy()
+            else:
+                host = np.ascontiguousarray(arr)
+            if host.dtype.hasobject:
+                raise ValueError("object arrays are not supported")
+            header = _npy_header(host)
+            body = _host_bytes(host)
+            # the member's stream: the .npy header as a stored block, then the GPU's blocks
+            comp = _stored_block(header) + deflate_raw(arr if _is_torch(arr) else host)
+            crc = zlib.crc32(body, zlib.crc32(header)) & 0xFFFFFFFF
+            usize = len(header) + len(body)
+            if usize >= 0xFFFFFFFF or len(comp) >= 0xFFFFFFFF:
+                raise ValueError("array too large for a zip member without zip64")
+            fname = (name + ".npy").encode()
+            offset = fh.tell() - start
+            # local file header: version 20, no flags, method 8 (deflate), DOS time/date 0 / 1980-01-01
+            fh.write(struct.pack("<IHHHHHIIIHH", 0x04034B50, 20, 0, 8, 0, 0x21, crc, len(comp), usize, len(fname), 0))
+            fh.write(fname)
+            fh.write(comp)
+            central.append(struct.pack("<IHHHHHHIIIHHHHHII", 0x02014B50, 20, 20, 0, 8, 0, 0x21, crc, len(comp), usize,
+                                       len(fname), 0, 0, 0, 0, 0, offset) + fname)
+        cd_off = fh.tell() - start
+        cd = b"".join(central)
+        fh.write(cd)
+        fh.write(struct.pack("<IHHHHIIH", 0x06054B50, 0, 0, len(central), len(central), len(cd), cd_off, 0))
+    finally:
+        if own:
+            fh.close()
