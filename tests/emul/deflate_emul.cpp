@@ -36,17 +36,37 @@ extern "C" long long dfl_emul(const uint8_t* src, long long n, int piece, int NT
     for (int tid = 0; tid < NT; ++tid) {
       dfl::CountVisitor cv;
       cv.init(hist);
-      dfl::parse_piece(src, S(tid), E(tid), cv);
+      dfl::parse_piece(src, n, S(tid), E(tid), cv);
       cv.flush();
     }
-    for (int i = 0; i < dfl::NLIT; ++i)
-      if (hist[i]) scratch.sorted[dfl::rank_of(hist, dfl::NLIT, i)] = uint16_t(i);
-    dfl::segment_build(hist, scratch, codes, hdr);
+    // the kernel's CTA-parallel construction, one step after the other ...
+    scratch.m = 0;
+    scratch.hi = 0;
+    for (int i = 0; i <= dfl::MAX_LIT_BITS; ++i) scratch.cnt[i] = 0;
+    for (int tid = 0; tid < NT; ++tid) dfl::par_rank(hist, dfl::NLIT, scratch, codes.code, codes.len, tid, NT);
+    for (int tid = 0; tid < NT; ++tid) dfl::par_tree(scratch, tid);
+    for (int tid = 0; tid < NT; ++tid) dfl::par_count(scratch, dfl::MAX_LIT_BITS, tid, NT);
+    for (int tid = 0; tid < NT; ++tid) dfl::par_limit(scratch, dfl::MAX_LIT_BITS, tid);
+    for (int tid = 0; tid < NT; ++tid) dfl::par_lengths(scratch, dfl::MAX_LIT_BITS, codes.len, tid, NT);
+    for (int tid = 0; tid < NT; ++tid) dfl::par_codes(scratch, dfl::NLIT, codes.len, codes.code, tid, NT);
+    dfl::segment_header(scratch, codes, hdr);
+    {
+      // ... gives the code of the serial build_code()
+      dfl::Codes c2;
+      dfl::Header h2;
+      dfl::BuildScratch s2;
+      int hi = 0;
+      for (int i = 0; i < dfl::NLIT; ++i)
+        if (hist[i]) { s2.sorted[dfl::rank_of(hist, dfl::NLIT, i)] = uint16_t(i); hi = i; }
+      dfl::segment_build(hist, s2, c2, h2);
+      if (memcmp(c2.len, codes.len, sizeof c2.len) || memcmp(c2.code, codes.code, sizeof c2.code)) return -4;
+      if (h2.bits != hdr.bits || h2.ntok != hdr.ntok || int(scratch.hi) != hi) return -5;
+    }
     for (int tid = 0; tid < NT; ++tid) {
       dfl::SizeVisitor sv;
       sv.len = codes.len;
       sv.bits = 0;
-      dfl::parse_piece(src, S(tid), E(tid), sv);
+      dfl::parse_piece(src, n, S(tid), E(tid), sv);
       off[tid] = sv.bits;
     }
     long long acc = hdr.bits;
@@ -73,7 +93,7 @@ extern "C" long long dfl_emul(const uint8_t* src, long long n, int piece, int NT
         dfl::EmitVisitor ev;
         ev.c = &codes;
         ev.bw = &bw;
-        dfl::parse_piece(src, S(tid), E(tid), ev);
+        dfl::parse_piece(src, n, S(tid), E(tid), ev);
         if (tid == 0 && bw.bitpos() != (NT > 1 ? (long long)off[1] : bw.bitpos()) && S(1) < E(1)) return -2;
         if (tid == NT - 1) {
           dfl::segment_close(codes, bw);

@@ -56,30 +56,48 @@ DFL_HD void length_symbol(int L, int* sym, int* ebits, int* eval) {
 // Tokens of the piece [s, e) of src[0, n): a byte equal to its predecessor starts a match of
 // distance 1 when at least MIN_MATCH bytes repeat (the predecessor may lie in the previous piece
 // or segment: the decoder has produced it by then).  V::lit(byte) / V::match(length).
-// src must be 8-byte aligned.
+// src must be 8-byte aligned.  The input is read as aligned 64-bit words kept in a register (one
+// load per 8 bytes: the pieces of a warp's threads lie `piece` bytes apart, so every load costs one
+// L1 wavefront per thread); bytes past n are never touched.
+#if defined(__CUDA_ARCH__)
+#define DFL_CTZ64(x) (__ffsll((long long)(x)) - 1)
+#else
+#define DFL_CTZ64(x) __builtin_ctzll(x)
+#endif
+
+DFL_HD uint64_t load_word(const uint8_t* src, long long n, long long base) {
+  if (base + 8 <= n) return *reinterpret_cast<const uint64_t*>(src + base);
+  uint64_t x = 0;
+  for (int k = 0; base + k < n; ++k) x |= uint64_t(src[base + k]) << (8 * k);
+  return x;
+}
+
 template <class V>
-DFL_HD void parse_piece(const uint8_t* src, long long s, long long e, V& v) {
+DFL_HD void parse_piece(const uint8_t* src, long long n, long long s, long long e, V& v) {
   long long p = s;
   int prev = p > 0 ? int(src[p - 1]) : -1;
+  long long wbase = -8;
+  uint64_t w = 0;
   while (p < e) {
-    const int b = src[p];
+    const long long base = p & ~7ll;
+    if (base != wbase) { w = load_word(src, n, base); wbase = base; }
+    const int b = int((w >> (8 * int(p & 7))) & 0xff);
     if (b == prev) {
       const long long rem = e - p;
       const int lim = rem < MAX_MATCH ? int(rem) : MAX_MATCH;
       const uint64_t splat = 0x0101010101010101ull * uint64_t(prev);
-      int L = 1;
-      while (L < lim) {
-        if ((((p + L) & 7) == 0) && L + 8 <= lim) {
-          const uint64_t x = *reinterpret_cast<const uint64_t*>(src + p + L) ^ splat;
-          if (x == 0) { L += 8; continue; }
-          int z = 0;                                   // index of the first differing byte (little endian)
-          for (uint64_t t = x; !(t & 0xff); t >>= 8) ++z;
-          L += z;
-          break;
-        }
-        if (src[p + L] != prev) break;
-        ++L;
+      int L = 0;
+      for (;;) {
+        const int off = int((p + L) & 7);
+        const uint64_t x = (w ^ splat) >> (8 * off);
+        const int avail = 8 - off;
+        const int z = x ? (DFL_CTZ64(x) >> 3) : avail;    // a differing byte lies inside the `avail` valid ones
+        L += z;
+        if (z < avail || L >= lim) break;
+        wbase += 8;
+        w = load_word(src, n, wbase);
       }
+      if (L > lim) L = lim;
       if (L >= MIN_MATCH) { v.match(L); p += L; continue; }
     }
     v.lit(b);
@@ -194,6 +212,12 @@ DFL_HD int rank_of(const uint32_t* freq, int n, int i) {
 
 struct BuildScratch {          // n <= NLIT
   uint16_t sorted[NLIT];       // symbols by ascending (frequency, symbol), filled through rank_of()
+  uint32_t sw[NLIT];           // their frequencies in that order (parallel construction only)
+  uint32_t cnt[MAX_LIT_BITS + 1];    // codes per length           "
+  uint32_t next[MAX_LIT_BITS + 2];   // first code of each length  "
+  uint32_t cum[MAX_LIT_BITS + 1];    // codes of length <= i       "
+  uint32_t m;                        // used symbols               "
+  uint32_t hi;                       // largest used symbol        "
   uint32_t iw[NLIT];           // weights of the internal nodes in creation order
   uint16_t ipar[NLIT];         // parent (internal node index) of internal node
   uint16_t lpar[NLIT];         // parent of leaf sorted[k]
@@ -201,6 +225,9 @@ struct BuildScratch {          // n <= NLIT
 };
 
 DFL_HD uint32_t bit_reverse(uint32_t v, int n) {
+#if defined(__CUDA_ARCH__)
+  return n ? __brev(v) >> (32 - n) : 0u;
+#endif
   uint32_t r = 0;
   for (int i = 0; i < n; ++i) { r = (r << 1) | (v & 1); v >>= 1; }
   return r;
@@ -257,6 +284,117 @@ DFL_HD void build_code(const uint32_t* freq, int n, int m, int maxbits, BuildScr
   for (int i = 0; i < n; ++i) {
     const int l = len[i];
     code[i] = l ? uint16_t(bit_reverse(next[l]++, l)) : uint16_t(0);
+  }
+}
+
+// ---- the same construction in CTA-parallel steps ---------------------------------------------------
+//
+// One thread executes an instruction every ~10 cycles when each depends on the last, so a serial
+// build_code() of the 286-symbol literal/length code holds the other 511 threads at a barrier for
+// longer than they take to parse the segment.  The steps below leave only the two-queue merge and
+// the walk over the internal nodes to one thread; every function is called by all `nt` threads with
+// their `tid`, with a CTA barrier between consecutive steps.  Results equal build_code()'s.
+// S.m, S.hi and S.cnt[] must be zero before par_rank().
+
+#if defined(__CUDA_ARCH__)
+#define DFL_ATOMIC_MAX(ptr, val) atomicMax((ptr), (val))
+#else
+#define DFL_ATOMIC_MAX(ptr, val) (*(ptr) = *(ptr) > (val) ? *(ptr) : (val))
+#endif
+
+DFL_HD void par_rank(const uint32_t* freq, int n, BuildScratch& S, uint16_t* code, uint8_t* len, int tid, int nt) {
+  for (int i = tid; i < n; i += nt) {
+    len[i] = 0;
+    code[i] = 0;
+    const uint32_t f = freq[i];
+    if (f) {
+      const int r = rank_of(freq, n, i);
+      S.sorted[r] = uint16_t(i);
+      S.sw[r] = f;
+      DFL_ATOMIC_ADD(&S.m, 1u);
+      DFL_ATOMIC_MAX(&S.hi, uint32_t(i));
+    }
+  }
+}
+
+DFL_HD void par_tree(BuildScratch& S, int tid) {         // two-queue merge, depths of the internal nodes
+  if (tid != 0) return;
+  const int m = int(S.m);
+  if (m < 2) return;
+  const uint32_t INF = 0xffffffffu;                      // above any weight: a segment has < 2^32 symbols
+  int li = 0, ii = 0, ni = 0;
+  uint32_t lw = S.sw[0], ih = INF;                       // heads of the leaf and the internal-node queue
+  for (int k = 0; k < m - 1; ++k) {
+    uint32_t wsum = 0;
+    for (int pick = 0; pick < 2; ++pick) {
+      if (li < m && lw <= ih) {
+        wsum += lw; S.lpar[li] = uint16_t(ni); ++li;
+        lw = li < m ? S.sw[li] : INF;
+      } else {
+        wsum += ih; S.ipar[ii] = uint16_t(ni); ++ii;
+        ih = ii < ni ? S.iw[ii] : INF;
+      }
+    }
+    S.iw[ni] = wsum;
+    if (ii == ni) ih = wsum;                              // the queue was empty: the new node is its head
+    ++ni;
+  }
+  S.idepth[m - 2] = 0;                                    // the root
+  for (int j = m - 3; j >= 0; --j) {
+    const int d = S.idepth[S.ipar[j]] + 1;
+    S.idepth[j] = uint8_t(d > 62 ? 62 : d);
+  }
+}
+
+DFL_HD void par_count(BuildScratch& S, int maxbits, int tid, int nt) {
+  const int m = int(S.m);
+  if (m < 2) return;
+  for (int k = tid; k < m; k += nt) {
+    int d = S.idepth[S.lpar[k]] + 1;
+    if (d > maxbits) d = maxbits;
+    DFL_ATOMIC_ADD(&S.cnt[d], 1u);
+  }
+}
+
+DFL_HD void par_limit(BuildScratch& S, int maxbits, int tid) {   // Kraft sum to exactly one, first codes, prefix counts
+  if (tid != 0) return;
+  const int m = int(S.m);
+  if (m < 2) {
+    for (int i = 0; i <= maxbits; ++i) S.cnt[i] = 0;
+    S.cnt[1] = uint32_t(m);
+  } else {
+    uint32_t total = 0;
+    for (int i = maxbits; i > 0; --i) total += S.cnt[i] << (maxbits - i);
+    while (total != (1u << maxbits)) {
+      --S.cnt[maxbits];
+      for (int i = maxbits - 1; i > 0; --i)
+        if (S.cnt[i]) { --S.cnt[i]; S.cnt[i + 1] += 2; break; }
+      --total;
+    }
+  }
+  S.next[0] = 0; S.next[1] = 0;
+  for (int i = 2; i <= maxbits; ++i) S.next[i] = (S.next[i - 1] + S.cnt[i - 1]) << 1;
+  S.cum[0] = 0;
+  for (int i = 1; i <= maxbits; ++i) S.cum[i] = S.cum[i - 1] + S.cnt[i];
+}
+
+DFL_HD void par_lengths(const BuildScratch& S, int maxbits, uint8_t* len, int tid, int nt) {
+  const int m = int(S.m);
+  for (int k = tid; k < m; k += nt) {
+    const uint32_t r = uint32_t(m - 1 - k);              // rank by descending frequency: the shortest codes first
+    int i = 1;
+    while (i < maxbits && r >= S.cum[i]) ++i;
+    len[S.sorted[k]] = uint8_t(i);
+  }
+}
+
+DFL_HD void par_codes(const BuildScratch& S, int n, const uint8_t* len, uint16_t* code, int tid, int nt) {
+  for (int i = tid; i < n; i += nt) {
+    const int l = len[i];
+    if (!l) continue;
+    uint32_t c = S.next[l];
+    for (int j = 0; j < i; ++j) c += len[j] == l;         // canonical order: by symbol inside a length
+    code[i] = uint16_t(bit_reverse(c, l));
   }
 }
 
@@ -369,10 +507,17 @@ DFL_HD void stored_copy(const uint8_t* seg, long long n, long long s, long long 
 // hist: frequencies of the literal/length symbols of the segment (EOB counted once, so at least
 // two symbols are used); S.sorted: the used symbols by ascending (frequency, symbol).  Builds the literal/length
 // code, the header tokens and the code-length code.
+DFL_HD void segment_header(BuildScratch& S, const Codes& c, Header& h);
+
 DFL_HD void segment_build(const uint32_t* hist, BuildScratch& S, Codes& c, Header& h) {
   int m = 0;
   for (int i = 0; i < NLIT; ++i) m += hist[i] != 0;
   build_code(hist, NLIT, m, MAX_LIT_BITS, S, c.code, c.len);
+  segment_header(S, c, h);
+}
+
+// the block header for the finished literal/length code (one thread)
+DFL_HD void segment_header(BuildScratch& S, const Codes& c, Header& h) {
   header_tokens(c.len, h);
   int used = 0;
   for (int i = 0; i < NCL; ++i) used += h.clfreq[i] != 0;

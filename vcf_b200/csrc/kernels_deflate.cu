@@ -7,8 +7,8 @@
 // the drop-in property is "the reference's decoder returns the same bytes".
 //
 //   deflate_segments_kernel  one CTA per segment of NT pieces.  Phase 1: every thread parses its
-//       piece (run-length parse, deflate_core.cuh) into a shared histogram.  Phase 2: rank sort
-//       of the used symbols by all threads, Huffman code + block header by thread 0.  Phase 3:
+//       piece (run-length parse, deflate_core.cuh) into a shared histogram.  Phase 2: Huffman
+//       code in CTA-parallel steps (rank sort, serial two-queue merge, lengths, canonical codes), block header by thread 0.  Phase 3:
 //       every thread sizes its piece under the code; exclusive scan -> bit offsets; the segment
 //       falls back to stored blocks when those are smaller.  Phase 4: the CTA zeroes exactly the
 //       bytes the block takes, every thread writes its tokens at its bit offset (first and last
@@ -17,6 +17,8 @@
 //   deflate_gather_kernel    copies every segment's bytes to its place in the output stream.
 #include "common.cuh"
 #include "deflate_core.cuh"
+
+#include <stdlib.h>
 
 namespace vcfb {
 namespace {
@@ -34,9 +36,15 @@ struct Plan {
 
 Plan make_plan(unsigned long long n) {
   Plan p;
-  // multiples of the longest match (258): a piece that lies inside a long run becomes matches of
-  // length 258 (symbol 285, no extra bits), as in a sequential parse
-  p.piece = n >= (64ull << 20) ? 4 * dfl::MAX_MATCH : n >= (4ull << 20) ? 2 * dfl::MAX_MATCH : dfl::MAX_MATCH;
+  // a multiple of the longest match (258): a piece that lies inside a long run becomes matches of
+  // length 258 (symbol 285, no extra bits), as in a sequential parse.  258 itself: the time of a
+  // segment is the serial walk of a thread over its piece, and longer pieces were slower at every
+  // input size on the B200 (profiles/r1h_deflate_piece_sweep.txt) while saving < 1 % of the stream.
+  p.piece = dfl::MAX_MATCH;
+  if (const char* env = getenv("VCFB_DEFLATE_PIECE")) {      // measurement knob: multiples of 258 only
+    const int k = atoi(env) / dfl::MAX_MATCH;
+    if (k >= 1 && k <= 16) p.piece = k * dfl::MAX_MATCH;
+  }
   p.seg_bytes = (long long)NT * p.piece;
   p.nseg = (long long)((n + p.seg_bytes - 1) / p.seg_bytes);
   p.stride = (dfl::stored_size(p.seg_bytes) + 15) / 16 * 16 + 16;
@@ -54,6 +62,7 @@ struct SegShared {
   dfl::Header hdr;
   dfl::BuildScratch scratch;
   uint32_t off[NT];
+  uint32_t wsum[NT / 32];
   long long total_bytes;
   int stored;
 };
@@ -72,6 +81,8 @@ deflate_segments_kernel(const uint8_t* __restrict__ src, long long n, int piece,
   uint8_t* out = regions + seg * stride;
 
   for (int i = tid; i < 288; i += NT) sh.hist[i] = 0;
+  if (tid <= dfl::MAX_LIT_BITS) sh.scratch.cnt[tid] = 0;
+  if (tid == 32) { sh.scratch.m = 0; sh.scratch.hi = 0; }
   __syncthreads();
   if (tid == 0) sh.hist[dfl::EOB] = 1;
 
@@ -79,16 +90,26 @@ deflate_segments_kernel(const uint8_t* __restrict__ src, long long n, int piece,
   {
     dfl::CountVisitor cv;
     cv.init(sh.hist);
-    dfl::parse_piece(src, s, e, cv);
+    dfl::parse_piece(src, n, s, e, cv);
     cv.flush();
   }
   __syncthreads();
 
   // phase 2: code construction
-  for (int i = tid; i < dfl::NLIT; i += NT)
-    if (sh.hist[i]) sh.scratch.sorted[dfl::rank_of(sh.hist, dfl::NLIT, i)] = uint16_t(i);
+  //  (the steps of deflate_core.cuh: only the two-queue merge, the Kraft fix and the header are serial)
+  dfl::par_rank(sh.hist, dfl::NLIT, sh.scratch, sh.codes.code, sh.codes.len, tid, NT);
   __syncthreads();
-  if (tid == 0) dfl::segment_build(sh.hist, sh.scratch, sh.codes, sh.hdr);
+  dfl::par_tree(sh.scratch, tid);
+  __syncthreads();
+  dfl::par_count(sh.scratch, dfl::MAX_LIT_BITS, tid, NT);
+  __syncthreads();
+  dfl::par_limit(sh.scratch, dfl::MAX_LIT_BITS, tid);
+  __syncthreads();
+  dfl::par_lengths(sh.scratch, dfl::MAX_LIT_BITS, sh.codes.len, tid, NT);
+  __syncthreads();
+  dfl::par_codes(sh.scratch, dfl::NLIT, sh.codes.len, sh.codes.code, tid, NT);
+  __syncthreads();
+  if (tid == 0) dfl::segment_header(sh.scratch, sh.codes, sh.hdr);
   __syncthreads();
 
   // phase 3: sizes and bit offsets
@@ -96,22 +117,42 @@ deflate_segments_kernel(const uint8_t* __restrict__ src, long long n, int piece,
     dfl::SizeVisitor sv;
     sv.len = sh.codes.len;
     sv.bits = 0;
-    dfl::parse_piece(src, s, e, sv);
+    dfl::parse_piece(src, n, s, e, sv);
     sh.off[tid] = sv.bits;
   }
   __syncthreads();
-  if (tid == 0) {
-    long long acc = sh.hdr.bits;
-    for (int t = 0; t < NT; ++t) {
-      const uint32_t b = sh.off[t];
-      sh.off[t] = uint32_t(acc);
-      acc += b;
+  {
+    // exclusive scan of the pieces' bit counts (a segment stays below 2^32 bits): warp shuffles,
+    // then the 16 warp totals
+    const int lane = tid & 31, wid = tid >> 5;
+    const uint32_t mine = sh.off[tid];
+    uint32_t incl = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
     }
-    const long long dyn = dfl::dynamic_size(sh.hdr, sh.codes, acc - sh.hdr.bits);
-    const long long st = dfl::stored_size(nseg);
-    sh.stored = dyn >= st;
-    sh.total_bytes = sh.stored ? st : dyn;
-    seg_size[seg] = uint32_t(sh.total_bytes);
+    if (lane == 31) sh.wsum[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      const uint32_t v = lane < NT / 32 ? sh.wsum[lane] : 0u;
+      uint32_t wi = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, wi, d);
+        if (lane >= d) wi += t;
+      }
+      if (lane < NT / 32) sh.wsum[lane] = wi - v;
+      if (lane == 31) {
+        const long long dyn = dfl::dynamic_size(sh.hdr, sh.codes, (long long)wi);
+        const long long st = dfl::stored_size(nseg);
+        sh.stored = dyn >= st;
+        sh.total_bytes = sh.stored ? st : dyn;
+        seg_size[seg] = uint32_t(sh.total_bytes);
+      }
+    }
+    __syncthreads();
+    sh.off[tid] = uint32_t(sh.hdr.bits) + sh.wsum[wid] + (incl - mine);
   }
   __syncthreads();
 
@@ -133,7 +174,7 @@ deflate_segments_kernel(const uint8_t* __restrict__ src, long long n, int piece,
     dfl::EmitVisitor ev;
     ev.c = &sh.codes;
     ev.bw = &bw;
-    dfl::parse_piece(src, s, e, ev);
+    dfl::parse_piece(src, n, s, e, ev);
     if (tid == NT - 1) dfl::segment_close(sh.codes, bw);
     bw.finish();
   }
