@@ -145,6 +145,53 @@ def test_plugin_against_the_real_reference_chain_cpu():
 
 
 @pytest.mark.gpu
+def test_cli_with_the_gpu_entropy_stage():
+    """-c z_lib-B200 (vcf_b200/plugin/z_lib-B200.py, the drop-in of src/z_lib.py): the code-stream is
+    an .npz whose deflate stream came from the GPU; np.load -- what src/z_lib.py:25-29 calls -- and the
+    decoder read it."""
+    img = O.synthetic_frame(272, 400, 33, "natural")
+    _write_png("/tmp/original.png", img)
+    for f in ("/tmp/encoded.npz", "/tmp/encoded_shape.bin", "/tmp/decoded.png"):
+        if os.path.exists(f):
+            os.remove(f)
+    r = _run(STUB, PLUGIN, "encode", "-q", "16", "-c", "z_lib-B200")
+    assert r.returncode == 0, r.stderr[-2000:]
+    idx = np.load("/tmp/encoded.npz")["a"]
+    assert idx.dtype == np.uint8 and np.array_equal(idx, O.encode_array(img, B=8, q=16))
+    import zipfile
+    info = zipfile.ZipFile("/tmp/encoded.npz").infolist()
+    assert [i.filename for i in info] == ["a.npy"] and info[0].compress_type == zipfile.ZIP_DEFLATED
+    assert info[0].compress_size < idx.size // 4
+    r = _run(STUB, PLUGIN, "decode", "-q", "16", "-c", "z_lib-B200")
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert np.array_equal(_read_png("/tmp/decoded.png"), O.decode_array(idx, img.shape, B=8, q=16))
+    # and the stock entropy stage of the chain reads the same file
+    r = _run(STUB, PLUGIN, "decode", "-q", "16")
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert np.array_equal(_read_png("/tmp/decoded.png"), O.decode_array(idx, img.shape, B=8, q=16))
+
+
+@pytest.mark.skipif(not os.path.isdir(REF_SRC), reason="reference only present in the build container")
+def test_entropy_plugin_in_the_real_reference_chain_cpu():
+    """-c z_lib-B200 inside the reference's own chain: the module takes z_lib's place in the MRO
+    (src/no_filter.py:21) and refuses to compress without a GPU."""
+    shims = os.path.join(ROOT, "oracle", "shims")
+    code = ("import importlib, sys; sys.argv=['x','encode','-c','z_lib-B200'];"
+            "m = importlib.import_module('2D-DCT-B200'); import parser; c = m.CoDec(parser.parser.parse_known_args()[0]);"
+            "print([k.__module__ for k in type(c).__mro__][:6], c.file_extension);"
+            "import numpy as np\n"
+            "try: c.compress(np.zeros((8, 8, 3), np.uint8))\n"
+            "except Exception as e: print('refused:', e)")
+    r = _run(REF_SRC, "-c", code, extra_path=(shims,))
+    assert r.returncode == 0, r.stderr[-1500:]
+    assert "'2D-DCT-B200', 'YCoCg', 'deadzone', 'no_filter', 'z_lib-B200', 'entropy_image_coding'" in r.stdout
+    assert ".npz" in r.stdout
+    from vcf_b200 import _lib
+    if _lib.lib().vcfb_device_count() == 0:
+        assert "refused:" in r.stdout and "no CPU fallback" in r.stdout
+
+
+@pytest.mark.gpu
 def test_batched_iii_driver_equals_per_frame_loop():
     """vcf_b200/plugin/III-B200.py: the whole sequence as one GPU batch must write the same
     files as the per-frame loop of src/III.py:132-144 (and the intended :96-104)."""

@@ -44,6 +44,13 @@ class CoDec:
         self.encoding = args.subparser_name == "encode"
         self.QSS = args.QSS
         self.total_input_size = self.total_output_size = 0
+        # -c <module>: another entropy codec (the reference makes it the base class, src/no_filter.py:21;
+        # the stand-in delegates to an instance)
+        self.entropy = None
+        if getattr(args, "entropy_image_codec", "npz_zlib") != "npz_zlib":
+            import importlib
+            self.entropy = importlib.import_module(args.entropy_image_codec).CoDec(args)
+            self.file_extension = self.entropy.file_extension
 
     def bye(self):
         pass
@@ -76,11 +83,15 @@ class CoDec:
 
     # ---- entropy codec ----------------------------------------------------------------
     def compress(self, img):
+        if self.entropy is not None:
+            return self.entropy.compress(img)
         buf = io.BytesIO()
         np.savez_compressed(buf, a=img)
         return buf
 
     def decompress(self, data):
+        if self.entropy is not None:
+            return self.entropy.decompress(data)
         return np.load(io.BytesIO(data))["a"]
 
     # ---- decoding filter ----------------------------------------------------------------
