@@ -109,8 +109,9 @@ deflate_segments_kernel(const uint8_t* __restrict__ src, long long n, int piece,
   __syncthreads();
   dfl::par_codes(sh.scratch, dfl::NLIT, sh.codes.len, sh.codes.code, tid, NT);
   __syncthreads();
+  // the block header needs one thread and nothing below needs it before the scan: no barrier, the
+  // other warps size their pieces meanwhile
   if (tid == 0) dfl::segment_header(sh.scratch, sh.codes, sh.hdr);
-  __syncthreads();
 
   // phase 3: sizes and bit offsets
   {
