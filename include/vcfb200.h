@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define VCFB_VERSION 120 /* 0.2.0: + vcfb_deflate_dev, vcfb_deflate_bound, vcfb_deflate_workspace (0.1.1: vcfb_launch_count, motion estimation) */
+#define VCFB_VERSION 120 /* 0.2.0: + vcfb_deflate_dev, vcfb_deflate_bound, vcfb_deflate_workspace, vcfb_crc32_dev (0.1.1: vcfb_launch_count, motion estimation) */
 
 /* error codes */
 #define VCFB_OK 0
@@ -180,6 +180,13 @@ size_t vcfb_deflate_bound(size_t n_bytes);
 size_t vcfb_deflate_workspace(size_t n_bytes);
 int vcfb_deflate_dev(const uint8_t* src, size_t n_bytes, uint8_t* dst, size_t dst_capacity,
                      uint64_t* out_bytes, void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* CRC-32 (zip / zlib / PNG polynomial, the value zlib.crc32 returns) of n_bytes bytes on the device:
+ * the checksum a zip member carries next to its deflate stream (np.savez_compressed,
+ * src/z_lib.py:19-23).  src 8-byte aligned; out_crc one uint32 on the device.  Asynchronous on
+ * cuda_stream (a 4-byte memset and one kernel).  CRCs of consecutive parts combine on the host:
+ * vcf_b200.entropy.crc32_combine. */
+int vcfb_crc32_dev(const uint8_t* src, size_t n_bytes, uint32_t* out_crc, void* cuda_stream);
 
 /* Host-buffer convenience layer (what a numpy caller binds).  A context owns one
  * CUDA stream plus pinned and device staging buffers that grow on demand. */

@@ -112,3 +112,17 @@ extern "C" long long dfl_emul(const uint8_t* src, long long n, int piece, int NT
   if (n_stored_segments) *n_stored_segments = stored_count;
   return pos;
 }
+
+// CRC-32 of src[0, n) the way crc32_kernel (vcf_b200/csrc/kernels_deflate.cu) forms it: chunks of
+// `chunk` bytes, one per "thread", XOR of their shifted CRCs.
+#include "../../vcf_b200/csrc/crc32_core.cuh"
+
+extern "C" uint32_t crc_emul(const uint8_t* src, long long n, int chunk) {
+  uint32_t tab[256];
+  for (uint32_t i = 0; i < 256; ++i) tab[i] = crc::table_entry(i);
+  crc::Powers P;
+  crc::make_powers(P);
+  uint32_t total = 0;
+  for (long long s = 0; s < n; s += chunk) total ^= crc::chunk_term(src, n, s, std::min(n, s + chunk), tab, P);
+  return total;
+}

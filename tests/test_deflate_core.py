@@ -121,3 +121,18 @@ def test_random_fuzz(emul):
         piece = int(rng.choice([8, 16, 64, 258, 516, 1032]))
         nt = int(rng.choice([1, 2, 7, 32, 512]))
         _roundtrip(emul, data, piece=piece, nt=nt)
+
+
+def test_crc32_in_chunks_equals_zlib(emul):
+    L = ctypes.CDLL(SO)
+    L.crc_emul.restype = ctypes.c_uint32
+    L.crc_emul.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int]
+    rng = np.random.default_rng(9)
+    for n in (0, 1, 2, 7, 8, 9, 255, 256, 511, 512, 513, 1000, 65536, 100003, 3_000_001):
+        data = rng.integers(0, 256, n + 16, dtype=np.uint8)
+        for lead in (0, 3):                                   # aligned and unaligned starts
+            view = np.ascontiguousarray(data[lead:lead + n])
+            for chunk in (512, 1, 13, 4096):
+                if chunk == 1 and n > 70000:
+                    continue
+                assert L.crc_emul(view.ctypes.data, n, chunk) == (zlib.crc32(view.tobytes()) & 0xFFFFFFFF), (n, lead, chunk)

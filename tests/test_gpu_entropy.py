@@ -144,3 +144,40 @@ def test_argument_errors():
     big = torch.zeros(L.vcfb_deflate_bound(1000), dtype=torch.uint8, device="cuda")
     with pytest.raises(VcfbError):
         _lib.check(L.vcfb_deflate_dev(x.data_ptr(), 1000, big.data_ptr(), big.numel(), n.data_ptr(), ws.data_ptr(), 8, None))
+
+
+def test_crc32_equals_zlib():
+    import torch
+    from vcf_b200 import _lib
+    from vcf_b200.entropy import crc32, crc32_combine
+    rng = np.random.default_rng(4)
+    for n in (0, 1, 7, 8, 9, 511, 512, 513, 4096, 100003, 512 * 256 * 3 + 5, 30_000_001):
+        data = rng.integers(0, 256, n, dtype=np.uint8)
+        assert crc32(data) == (zlib.crc32(data.tobytes()) & 0xFFFFFFFF), n
+        if n:
+            assert _lib.last_kernel() == "crc32"
+    x = torch.from_numpy(rng.integers(-500, 500, (33, 77, 3), dtype=np.int16)).cuda()
+    assert crc32(x) == (zlib.crc32(x.cpu().numpy().tobytes()) & 0xFFFFFFFF)
+    a, b = rng.integers(0, 256, 1000, dtype=np.uint8), rng.integers(0, 256, 77777, dtype=np.uint8)
+    assert crc32_combine(crc32(a), crc32(b), b.size) == (zlib.crc32(np.concatenate([a, b]).tobytes()) & 0xFFFFFFFF)
+
+
+def test_savez_compressed_from_cuda_tensors():
+    """The batched driver hands CUDA tensors over: no host copy of the array is made, and the zip
+    member's CRC-32 (checked by np.load / zipfile on reading) comes from the GPU."""
+    import zipfile
+    import torch
+    from vcf_b200.entropy import savez_compressed
+    rng = np.random.default_rng(6)
+    a = np.repeat(rng.integers(120, 136, 90000, dtype=np.uint8), rng.integers(1, 40, 90000))[:1_500_000].reshape(500, 1000, 3)
+    t = torch.from_numpy(a).cuda()
+    e = torch.zeros((0, 4), dtype=torch.float32, device="cuda")
+    fh = io.BytesIO()
+    savez_compressed(fh, a=t, k=(t.to(torch.int16) - 128), empty=e)
+    fh.seek(0)
+    assert zipfile.ZipFile(fh).testzip() is None            # every member's CRC-32 verifies
+    fh.seek(0)
+    z = np.load(fh)
+    assert z["a"].dtype == np.uint8 and np.array_equal(z["a"], a)
+    assert z["k"].dtype == np.int16 and np.array_equal(z["k"], a.astype(np.int16) - 128)
+    assert z["empty"].shape == (0, 4) and z["empty"].dtype == np.float32

@@ -17,6 +17,7 @@
 //   deflate_gather_kernel    copies every segment's bytes to its place in the output stream.
 #include "common.cuh"
 #include "deflate_core.cuh"
+#include "crc32_core.cuh"
 
 #include <stdlib.h>
 
@@ -234,6 +235,30 @@ deflate_gather_kernel(const uint8_t* __restrict__ regions, long long stride, con
   }
 }
 
+// CRC-32 of a byte array (crc32_core.cuh): one 512-byte chunk per thread and grid-stride step, the
+// chunk's finished CRC shifted to the end of the input, XOR over the grid.  *out is zero on entry.
+constexpr int CRC_NT = 256;
+constexpr int CRC_CHUNK = 512;
+
+__global__ void __launch_bounds__(CRC_NT)
+crc32_kernel(const uint8_t* __restrict__ src, long long n, crc::Powers P, uint32_t* __restrict__ out) {
+  __shared__ uint32_t tab[256];
+  __shared__ crc::Powers Ps;
+  tab[threadIdx.x] = crc::table_entry(threadIdx.x);
+  if (threadIdx.x < 32) Ps.x2n[threadIdx.x] = P.x2n[threadIdx.x];
+  __syncthreads();
+  const long long nchunks = (n + CRC_CHUNK - 1) / CRC_CHUNK;
+  uint32_t acc = 0;
+  for (long long c = (long long)blockIdx.x * CRC_NT + threadIdx.x; c < nchunks; c += (long long)gridDim.x * CRC_NT) {
+    const long long s = c * CRC_CHUNK;
+    const long long e = min(n, s + CRC_CHUNK);
+    acc ^= crc::chunk_term(src, n, s, e, tab, Ps);
+  }
+#pragma unroll
+  for (int d = 16; d; d >>= 1) acc ^= __shfl_xor_sync(0xffffffffu, acc, d);
+  if ((threadIdx.x & 31) == 0 && acc) atomicXor(out, acc);
+}
+
 }  // namespace
 }  // namespace vcfb
 
@@ -278,6 +303,27 @@ int vcfb_deflate_dev(const uint8_t* src, size_t n_bytes, uint8_t* dst, size_t ds
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "deflate_gather_kernel launch");
   }
+  return VCFB_OK;
+}
+
+int vcfb_crc32_dev(const uint8_t* src, size_t n_bytes, uint32_t* out_crc, void* cuda_stream) {
+  if (!out_crc) { set_error("output pointer is NULL"); return VCFB_E_ARG; }
+  if (n_bytes && !src) { set_error("input pointer is NULL"); return VCFB_E_ARG; }
+  if (n_bytes >= (1ull << 40)) { set_error("input too large"); return VCFB_E_ARG; }
+  if (reinterpret_cast<uintptr_t>(src) & 7) { set_error("vcfb_crc32_dev: src must be 8-byte aligned"); return VCFB_E_ARG; }
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(cuda_stream);
+  cudaError_t e = cudaMemsetAsync(out_crc, 0, sizeof(uint32_t), s);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+  if (!n_bytes) return VCFB_OK;                       // crc32 of nothing is 0
+  crc::Powers P;
+  crc::make_powers(P);
+  const long long nchunks = (long long)((n_bytes + CRC_CHUNK - 1) / CRC_CHUNK);
+  const long long want = (nchunks + CRC_NT - 1) / CRC_NT;
+  const unsigned grid = unsigned(want < 148 * 8 ? want : 148 * 8);
+  note_kernel("crc32");
+  crc32_kernel<<<grid, CRC_NT, 0, s>>>(src, (long long)n_bytes, P, out_crc);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "crc32_kernel launch");
   return VCFB_OK;
 }
 

@@ -12,9 +12,10 @@ deflate stream on the device; this module wraps it in the containers the referen
 * ``savez_compressed(f, a=x)`` .npz (zip, method 8)      -> ``np.load(f)['a']`` as in src/z_lib.py:25-29
 
 The streams are not byte-identical with zlib's (a different, run-length parse); what is kept is
-that the reference's decoder returns the same array.  Checksums (Adler-32 / CRC-32) are taken
-with the host's zlib over the host copy of the array.  There is no CPU fallback for the
-compression itself.
+that the reference's decoder returns the same array.  The CRC-32 of a zip member is taken on the
+GPU as well (``vcfb_crc32_dev``: a CUDA tensor is never copied to the host, only its stream and
+four bytes of checksum are); the Adler-32 of the zlib container with the host's zlib.  There is no
+CPU fallback for the compression itself.
 """
 from __future__ import annotations
 
@@ -64,6 +65,48 @@ def deflate_raw_dev(x):
     return dst, out_n
 
 
+def crc32_dev(x):
+    """Asynchronous on torch's current stream: one-element CUDA tensor (int64 holding the uint32)
+    with ``zlib.crc32`` of the bytes of ``x``."""
+    import torch
+    x = _as_device_bytes(x)
+    out = torch.zeros(1, dtype=torch.int64, device=x.device)      # the low 4 bytes are written
+    with torch.cuda.device(x.device):
+        check(_lib.lib().vcfb_crc32_dev(x.data_ptr(), x.numel(), out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    return out
+
+
+def crc32(x) -> int:
+    """``zlib.crc32(bytes of x)`` computed on the GPU."""
+    return int(crc32_dev(x).item()) & 0xFFFFFFFF
+
+
+_CRC_POLY = 0xEDB88320
+
+
+def _multmodp(a: int, b: int) -> int:
+    """a(x) * b(x) mod the CRC-32 polynomial; bit 31 is the coefficient of x^0 (csrc/crc32_core.cuh)."""
+    p = 0
+    m = 1 << 31
+    while m:
+        if a & m:
+            p ^= b
+        b = (b >> 1) ^ _CRC_POLY if b & 1 else b >> 1
+        m >>= 1
+    return p
+
+
+def crc32_combine(crc1: int, crc2: int, len2: int) -> int:
+    """CRC-32 of A || B from crc32(A), crc32(B) and len(B) (zlib's crc32_combine)."""
+    p, sq, n = 1 << 31, 1 << 30, 8 * len2          # x^0, x^1, exponent in bits
+    while n:
+        if n & 1:
+            p = _multmodp(sq, p)
+        sq = _multmodp(sq, sq)
+        n >>= 1
+    return _multmodp(p, crc1) ^ crc2
+
+
 def deflate_raw(x) -> bytes:
     """Raw deflate stream of the bytes of ``x`` (numpy array or torch tensor)."""
     dst, out_n = deflate_raw_dev(x)
@@ -83,10 +126,18 @@ def zlib_compress(x) -> bytes:
     return b"\x78\x9c" + raw + struct.pack(">I", zlib.adler32(_host_bytes(x)) & 0xFFFFFFFF)
 
 
-def _npy_header(a: np.ndarray) -> bytes:
+def _npy_header(dtype: np.dtype, shape) -> bytes:
+    """The .npy header np.save writes for a C-contiguous array of this dtype and shape."""
     fh = io.BytesIO()
-    np.lib.format.write_array_header_1_0(fh, np.lib.format.header_data_from_array_1_0(a))
+    np.lib.format.write_array_header_1_0(fh, {"descr": np.lib.format.dtype_to_descr(np.dtype(dtype)),
+                                              "fortran_order": False, "shape": tuple(int(d) for d in shape)})
     return fh.getvalue()
+
+
+def torch_empty_numpy_dtype(t) -> np.dtype:
+    """numpy dtype of a torch tensor, without touching its data"""
+    import torch
+    return torch.empty(0, dtype=t.dtype).numpy().dtype
 
 
 def _stored_block(data: bytes) -> bytes:
@@ -108,17 +159,23 @@ def savez_compressed(file, **arrays) -> None:
         central = []
         for name, arr in arrays.items():
             if _is_torch(arr):
-                host = arr.detach().cpu().numpy()
+                dtype = torch_empty_numpy_dtype(arr)
+                shape = tuple(arr.shape)
+                src = arr.detach().contiguous()
             else:
-                host = np.ascontiguousarray(arr)
-            if host.dtype.hasobject:
+                src = np.ascontiguousarray(arr)
+                dtype, shape = src.dtype, src.shape
+            if dtype.hasobject:
                 raise ValueError("object arrays are not supported")
-            header = _npy_header(host)
-            body = _host_bytes(host)
+            header = _npy_header(dtype, shape)
+            dev = _as_device_bytes(src)                    # one upload (numpy) or none (CUDA tensor)
+            dst, out_n = deflate_raw_dev(dev)
+            crc_body = crc32_dev(dev)
+            nbytes = int(out_n.item())
             # the member's stream: the .npy header as a stored block, then the GPU's blocks
-            comp = _stored_block(header) + deflate_raw(arr if _is_torch(arr) else host)
-            crc = zlib.crc32(body, zlib.crc32(header)) & 0xFFFFFFFF
-            usize = len(header) + len(body)
+            comp = _stored_block(header) + dst[:nbytes].cpu().numpy().tobytes()
+            crc = crc32_combine(zlib.crc32(header) & 0xFFFFFFFF, int(crc_body.item()) & 0xFFFFFFFF, dev.numel())
+            usize = len(header) + dev.numel()
             if usize >= 0xFFFFFFFF or len(comp) >= 0xFFFFFFFF:
                 raise ValueError("array too large for a zip member without zip64")
             fname = (name + ".npy").encode()
