@@ -203,15 +203,21 @@ def test_batched_iii_driver_equals_per_frame_loop():
             if os.path.exists("/tmp/encoded_%04d%s" % (i, ext)):
                 os.remove("/tmp/encoded_%04d%s" % (i, ext))
     iii = os.path.join(PLUGIN_DIR, "III-B200.py")
-    r = _run(STUB, iii, "encode", "-N", str(n), "-q", "16")
-    assert r.returncode == 0, r.stderr[-2000:]
-    r = _run(STUB, iii, "decode", "-N", str(n), "-q", "16")
-    assert r.returncode == 0, r.stderr[-2000:]
-    for i, f in enumerate(frames):
-        assert struct.unpack("iii", open("/tmp/encoded_%04d_shape.bin" % i, "rb").read()) == f.shape
-        idx = np.load("/tmp/encoded_%04d.npz" % i)["a"]
-        assert np.array_equal(idx, O.encode_array(f, 8, 16))
-        assert np.array_equal(_read_png("/tmp/decoded_%04d.png" % i), O.decode_array(idx, f.shape, 8, 16))
+    # with the chain's own entropy stage, and with the GPU one (indices stay in HBM, -c z_lib-B200)
+    for entropy_flags in ((), ("-c", "z_lib-B200")):
+        for i in range(n):
+            for ext in (".npz", "_shape.bin"):
+                if os.path.exists("/tmp/encoded_%04d%s" % (i, ext)):
+                    os.remove("/tmp/encoded_%04d%s" % (i, ext))
+        r = _run(STUB, iii, "encode", "-N", str(n), "-q", "16", *entropy_flags)
+        assert r.returncode == 0, r.stderr[-2000:]
+        r = _run(STUB, iii, "decode", "-N", str(n), "-q", "16", *entropy_flags)
+        assert r.returncode == 0, r.stderr[-2000:]
+        for i, f in enumerate(frames):
+            assert struct.unpack("iii", open("/tmp/encoded_%04d_shape.bin" % i, "rb").read()) == f.shape
+            idx = np.load("/tmp/encoded_%04d.npz" % i)["a"]
+            assert np.array_equal(idx, O.encode_array(f, 8, 16))
+            assert np.array_equal(_read_png("/tmp/decoded_%04d.png" % i), O.decode_array(idx, f.shape, 8, 16))
 
 
 @pytest.mark.gpu

@@ -51,6 +51,7 @@ class CoDec:
             import importlib
             self.entropy = importlib.import_module(args.entropy_image_codec).CoDec(args)
             self.file_extension = self.entropy.file_extension
+            self.accepts_device_arrays = getattr(self.entropy, "accepts_device_arrays", False)
 
     def bye(self):
         pass

@@ -159,12 +159,12 @@ class CoDec(CT.CoDec):
         dec = self._codec(decode=True)
         if getattr(self.args, "filter", "no_filter") == "no_filter":
             y_dev = dec.decode(k_dev, img.shape[:2])             # overlaps with the entropy stage below
-            decom_k = self.compress(k_dev.cpu().numpy())
+            decom_k = self.compress(k_dev if getattr(self, "accepts_device_arrays", False) else k_dev.cpu().numpy())
             output_size = self.encode_write_fn(decom_k, out_fn)
             y = CT.CoDec.filter(self, y_dev.cpu().numpy())
         else:
             _, yf = dec.decode(k_dev, img.shape[:2], return_float=True)
-            decom_k = self.compress(k_dev.cpu().numpy())
+            decom_k = self.compress(k_dev if getattr(self, "accepts_device_arrays", False) else k_dev.cpu().numpy())
             output_size = self.encode_write_fn(decom_k, out_fn)
             y = np.clip(CT.CoDec.filter(self, yf.cpu().numpy()), 0, 255).astype(np.uint8)
         return y, output_size

@@ -95,13 +95,22 @@ class CoDec:
                 tc._check_image(fr)
             if len({fr.shape for fr in frames}) != 1:
                 raise ValueError("all frames of a sequence must have the same shape")
-            idx = tc._codec().encode(np.ascontiguousarray(np.stack(frames)))    # one GPU batch
+            batch = np.ascontiguousarray(np.stack(frames))
+            if getattr(tc, "accepts_device_arrays", False):
+                # the entropy stage runs on the GPU too (-c z_lib-B200): the indices never leave HBM,
+                # only the code-streams come back
+                import torch
+                idx_dev = tc._codec().encode(torch.from_numpy(batch).cuda())       # one GPU batch
+                streams = [tc.compress(idx_dev[j]) for j in range(hi - lo)]
+            else:
+                idx = tc._codec().encode(batch)                                     # one GPU batch
+                streams = None
 
             def finish(j):
                 out_fn = f"{ENCODE_OUTPUT_PREFIX}_%04d" % (lo + j)
                 with open(f"{out_fn}_shape.bin", "wb") as file:
                     file.write(struct.pack("iii", *frames[j].shape))
-                return tc.encode_write_fn(tc.compress(idx[j]), out_fn)
+                return tc.encode_write_fn(streams[j] if streams is not None else tc.compress(idx[j]), out_fn)
             sizes = list(pool.map(finish, range(hi - lo)))
         logging.info(f"rank {rank}: frames [{lo},{hi}) -> {sum(sizes)} bytes")
         return sum(sizes)

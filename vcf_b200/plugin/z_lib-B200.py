@@ -37,6 +37,10 @@ from vcf_b200 import entropy  # noqa: E402
 
 class CoDec(EIC.CoDec):
 
+    # compress() also takes CUDA tensors: the GPU transform stages above (2D-DCT-B200, III-B200)
+    # check this and keep the indices in HBM instead of handing over a host copy
+    accepts_device_arrays = True
+
     def __init__(self, args):
         logging.debug(f"trace args={args}")
         super().__init__(args)
