@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define VCFB_VERSION 120 /* 0.2.0: + vcfb_deflate_dev, vcfb_deflate_bound, vcfb_deflate_workspace, vcfb_crc32_dev (0.1.1: vcfb_launch_count, motion estimation) */
+#define VCFB_VERSION 120 /* 0.2.0: + vcfb_deflate_dev, vcfb_deflate_bound, vcfb_deflate_workspace, vcfb_crc32_dev, vcfb_adler32_dev (0.1.1: vcfb_launch_count, motion estimation) */
 
 /* error codes */
 #define VCFB_OK 0
@@ -187,6 +187,12 @@ int vcfb_deflate_dev(const uint8_t* src, size_t n_bytes, uint8_t* dst, size_t ds
  * cuda_stream (a 4-byte memset and one kernel).  CRCs of consecutive parts combine on the host:
  * vcf_b200.entropy.crc32_combine. */
 int vcfb_crc32_dev(const uint8_t* src, size_t n_bytes, uint32_t* out_crc, void* cuda_stream);
+
+/* Adler-32 (RFC 1950; the value zlib.adler32 returns) of n_bytes bytes on the device: the checksum
+ * that closes a zlib stream -- the strips tifffile writes with compression='zlib', src/TIFF.py:23-31.
+ * src 8-byte aligned; out_adler one uint32 on the device; workspace16 16 bytes on the device, 8-byte
+ * aligned.  Asynchronous on cuda_stream (a memset and two kernels). */
+int vcfb_adler32_dev(const uint8_t* src, size_t n_bytes, uint32_t* out_adler, void* workspace16, void* cuda_stream);
 
 /* Host-buffer convenience layer (what a numpy caller binds).  A context owns one
  * CUDA stream plus pinned and device staging buffers that grow on demand. */

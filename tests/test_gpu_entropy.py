@@ -181,3 +181,46 @@ def test_savez_compressed_from_cuda_tensors():
     assert z["a"].dtype == np.uint8 and np.array_equal(z["a"], a)
     assert z["k"].dtype == np.int16 and np.array_equal(z["k"], a.astype(np.int16) - 128)
     assert z["empty"].shape == (0, 4) and z["empty"].dtype == np.float32
+
+
+def test_adler32_equals_zlib_and_zlib_stream_from_cuda_tensor():
+    import torch
+    from vcf_b200 import _lib
+    from vcf_b200.entropy import adler32, zlib_compress
+    rng = np.random.default_rng(8)
+    for n in (0, 1, 7, 8, 9, 15, 16, 17, 4099, 100003, 65521 * 8 + 3, 30_000_001):
+        data = rng.integers(0, 256, n, dtype=np.uint8)
+        assert adler32(data) == (zlib.adler32(data.tobytes()) & 0xFFFFFFFF), n
+        assert _lib.last_kernel() == "adler32"
+    ones = np.full(20_000_000, 255, np.uint8)               # the largest sums
+    assert adler32(ones) == (zlib.adler32(ones.tobytes()) & 0xFFFFFFFF)
+    x = torch.from_numpy(np.repeat(rng.integers(0, 256, 5000, dtype=np.uint8), rng.integers(1, 100, 5000))).cuda()
+    assert zlib.decompress(zlib_compress(x)) == x.cpu().numpy().tobytes()      # inflate checks the Adler-32
+
+
+def test_tiff_zlib_is_read_by_libtiff_and_pillow():
+    """The TIFF container of the reference's default entropy stage (src/TIFF.py:23-31); tifffile is
+    not installed here, libtiff (through OpenCV) and Pillow are the independent readers."""
+    import cv2
+    import torch
+    from vcf_b200.entropy import tiff_zlib
+    rng = np.random.default_rng(10)
+    smooth = np.repeat(rng.integers(100, 160, 70000, dtype=np.uint8), rng.integers(1, 30, 70000))
+    cases = [smooth[: 301 * 457 * 3].reshape(301, 457, 3), smooth[: 64 * 64].reshape(64, 64),
+             rng.integers(0, 256, (1, 1, 3), dtype=np.uint8),
+             (smooth[: 90 * 70 * 3].astype(np.uint16) * 257).reshape(90, 70, 3)]
+    for a in cases:
+        for src in ((a, torch.from_numpy(a).cuda()) if a.dtype == np.uint8 else (a,)):
+            t = tiff_zlib(src)
+            back = cv2.imdecode(np.frombuffer(t, np.uint8), cv2.IMREAD_UNCHANGED)
+            assert back is not None and back.dtype == a.dtype
+            if back.ndim == 3:
+                back = cv2.cvtColor(back, cv2.COLOR_BGR2RGB)
+            assert np.array_equal(back.reshape(a.shape), a)
+        if a.dtype == np.uint8:
+            from PIL import Image
+            assert np.array_equal(np.array(Image.open(io.BytesIO(tiff_zlib(a)))).reshape(a.shape), a)
+    with pytest.raises(ValueError):
+        tiff_zlib(np.zeros((4, 4, 3), np.float32))
+    with pytest.raises(ValueError):
+        tiff_zlib(np.zeros((4, 4, 2), np.uint8))

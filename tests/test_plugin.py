@@ -171,6 +171,25 @@ def test_cli_with_the_gpu_entropy_stage():
     assert np.array_equal(_read_png("/tmp/decoded.png"), O.decode_array(idx, img.shape, B=8, q=16))
 
 
+@pytest.mark.gpu
+def test_cli_with_the_gpu_tiff_stage():
+    """-c TIFF-B200 (vcf_b200/plugin/TIFF-B200.py, the drop-in of the chain's default src/TIFF.py):
+    the code-stream is a deflate TIFF whose strip came from the GPU; libtiff reads it."""
+    img = O.synthetic_frame(272, 400, 34, "natural")
+    _write_png("/tmp/original.png", img)
+    for f in ("/tmp/encoded.tif", "/tmp/encoded_shape.bin", "/tmp/decoded.png"):
+        if os.path.exists(f):
+            os.remove(f)
+    r = _run(STUB, PLUGIN, "encode", "-q", "16", "-c", "TIFF-B200")
+    assert r.returncode == 0, r.stderr[-2000:]
+    idx = cv2.cvtColor(cv2.imread("/tmp/encoded.tif", cv2.IMREAD_UNCHANGED), cv2.COLOR_BGR2RGB)
+    assert idx.dtype == np.uint8 and np.array_equal(idx, O.encode_array(img, B=8, q=16))
+    assert os.path.getsize("/tmp/encoded.tif") < idx.size // 4
+    r = _run(STUB, PLUGIN, "decode", "-q", "16", "-c", "TIFF-B200")
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert np.array_equal(_read_png("/tmp/decoded.png"), O.decode_array(idx, img.shape, B=8, q=16))
+
+
 @pytest.mark.skipif(not os.path.isdir(REF_SRC), reason="reference only present in the build container")
 def test_entropy_plugin_in_the_real_reference_chain_cpu():
     """-c z_lib-B200 inside the reference's own chain: the module takes z_lib's place in the MRO
@@ -187,6 +206,12 @@ def test_entropy_plugin_in_the_real_reference_chain_cpu():
     assert "'2D-DCT-B200', 'YCoCg', 'deadzone', 'no_filter', 'z_lib-B200', 'entropy_image_coding'" in r.stdout
     assert ".npz" in r.stdout
     from vcf_b200 import _lib
+    if _lib.lib().vcfb_device_count() == 0:
+        assert "refused:" in r.stdout and "no CPU fallback" in r.stdout
+    r = _run(REF_SRC, "-c", code.replace("z_lib-B200", "TIFF-B200"), extra_path=(shims,))
+    assert r.returncode == 0, r.stderr[-1500:]
+    assert "'2D-DCT-B200', 'YCoCg', 'deadzone', 'no_filter', 'TIFF-B200', 'entropy_image_coding'" in r.stdout
+    assert ".tif" in r.stdout
     if _lib.lib().vcfb_device_count() == 0:
         assert "refused:" in r.stdout and "no CPU fallback" in r.stdout
 

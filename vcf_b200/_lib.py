@@ -84,6 +84,8 @@ def lib():
     L.vcfb_deflate_dev.restype = i
     L.vcfb_crc32_dev.argtypes = [vp, sz, vp, vp]
     L.vcfb_crc32_dev.restype = i
+    L.vcfb_adler32_dev.argtypes = [vp, sz, vp, vp, vp]
+    L.vcfb_adler32_dev.restype = i
     _lib = L
     return L
 

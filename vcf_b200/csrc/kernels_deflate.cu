@@ -259,6 +259,54 @@ crc32_kernel(const uint8_t* __restrict__ src, long long n, crc::Powers P, uint32
   if ((threadIdx.x & 31) == 0 && acc) atomicXor(out, acc);
 }
 
+// Adler-32 (RFC 1950, the checksum that closes a zlib stream -- tifffile's zlib codec,
+// src/TIFF.py:23-31): A = 1 + sum b_i, B = n + sum (n - i) b_i, both mod 65521.  Eight bytes per
+// thread and grid-stride step; sums[0], sums[1] are zero on entry.
+constexpr unsigned ADLER_MOD = 65521u;
+
+__global__ void __launch_bounds__(256)
+adler32_sums_kernel(const uint8_t* __restrict__ src, long long n, unsigned long long* __restrict__ sums) {
+  const long long nw = n >> 3;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  unsigned long long s1 = 0, s2 = 0;
+  unsigned wgt = unsigned((unsigned long long)(n - 8 * i) % ADLER_MOD);     // (n - position of the word) mod 65521
+  const unsigned dec = unsigned((unsigned long long)(8 * stride) % ADLER_MOD);
+  for (; i < nw; i += stride) {
+    uint64_t w = *reinterpret_cast<const uint64_t*>(src + 8 * i);
+    unsigned sb = 0, sk = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const unsigned b = unsigned(w) & 0xffu;
+      sb += b;
+      sk += unsigned(k) * b;
+      w >>= 8;
+    }
+    s1 += sb;
+    s2 += (unsigned long long)wgt * sb + (unsigned long long)ADLER_MOD * 8u - sk;   // sk <= 7140 < 8 * 65521
+    wgt = wgt >= dec ? wgt - dec : wgt + ADLER_MOD - dec;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0)
+    for (long long p = nw << 3; p < n; ++p) { s1 += src[p]; s2 += (unsigned long long)(n - p) * src[p] % ADLER_MOD; }
+  s1 %= ADLER_MOD;
+  s2 %= ADLER_MOD;
+#pragma unroll
+  for (int d = 16; d; d >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, d);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, d);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(sums, s1);
+    atomicAdd(sums + 1, s2);
+  }
+}
+
+__global__ void adler32_finish_kernel(const unsigned long long* __restrict__ sums, long long n, uint32_t* __restrict__ out) {
+  const unsigned a = unsigned((1ull + sums[0]) % ADLER_MOD);
+  const unsigned b = unsigned(((unsigned long long)n % ADLER_MOD + sums[1]) % ADLER_MOD);
+  *out = (b << 16) | a;
+}
+
 }  // namespace
 }  // namespace vcfb
 
@@ -324,6 +372,30 @@ int vcfb_crc32_dev(const uint8_t* src, size_t n_bytes, uint32_t* out_crc, void* 
   crc32_kernel<<<grid, CRC_NT, 0, s>>>(src, (long long)n_bytes, P, out_crc);
   e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "crc32_kernel launch");
+  return VCFB_OK;
+}
+
+int vcfb_adler32_dev(const uint8_t* src, size_t n_bytes, uint32_t* out_adler, void* workspace16, void* cuda_stream) {
+  if (!out_adler || !workspace16) { set_error("output or workspace pointer is NULL"); return VCFB_E_ARG; }
+  if (n_bytes && !src) { set_error("input pointer is NULL"); return VCFB_E_ARG; }
+  if (n_bytes >= (1ull << 40)) { set_error("input too large"); return VCFB_E_ARG; }
+  if ((reinterpret_cast<uintptr_t>(src) & 7) || (reinterpret_cast<uintptr_t>(workspace16) & 7)) {
+    set_error("vcfb_adler32_dev: src and workspace must be 8-byte aligned"); return VCFB_E_ARG;
+  }
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(cuda_stream);
+  unsigned long long* sums = static_cast<unsigned long long*>(workspace16);
+  cudaError_t e = cudaMemsetAsync(sums, 0, 16, s);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+  const long long nw = (long long)(n_bytes >> 3);
+  const long long want = (nw + 256 * 8 - 1) / (256 * 8);           // about 8 words per thread
+  const unsigned grid = unsigned(want < 1 ? 1 : want < 148 * 8 ? want : 148 * 8);
+  note_kernel("adler32");
+  adler32_sums_kernel<<<grid, 256, 0, s>>>(src, (long long)n_bytes, sums);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "adler32_sums_kernel launch");
+  adler32_finish_kernel<<<1, 1, 0, s>>>(sums, (long long)n_bytes, out_adler);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "adler32_finish_kernel launch");
   return VCFB_OK;
 }
 

@@ -10,12 +10,13 @@ deflate stream on the device; this module wraps it in the containers the referen
 * ``deflate_raw(x)``          raw RFC 1951 stream        -> ``zlib.decompress(s, -15)``
 * ``zlib_compress(x)``        RFC 1950 (78 9C ... adler) -> ``zlib.decompress(s)``
 * ``savez_compressed(f, a=x)`` .npz (zip, method 8)      -> ``np.load(f)['a']`` as in src/z_lib.py:25-29
+* ``tiff_zlib(x)``            TIFF, one zlib strip       -> ``tifffile.imread`` as in src/TIFF.py:33-39
 
 The streams are not byte-identical with zlib's (a different, run-length parse); what is kept is
 that the reference's decoder returns the same array.  The CRC-32 of a zip member is taken on the
 GPU as well (``vcfb_crc32_dev``: a CUDA tensor is never copied to the host, only its stream and
-four bytes of checksum are); the Adler-32 of the zlib container with the host's zlib.  There is no
-CPU fallback for the compression itself.
+four bytes of checksum are), and so is the Adler-32 that closes a zlib stream
+(``vcfb_adler32_dev``).  There is no CPU fallback.
 """
 from __future__ import annotations
 
@@ -114,16 +115,84 @@ def deflate_raw(x) -> bytes:
     return dst[:n].cpu().numpy().tobytes()
 
 
-def _host_bytes(x) -> memoryview:
-    if _is_torch(x):
-        x = x.detach().cpu().numpy()
-    return memoryview(np.ascontiguousarray(x).reshape(-1).view(np.uint8))
+def adler32_dev(x):
+    """Asynchronous on torch's current stream: one-element CUDA tensor (int64 holding the uint32)
+    with ``zlib.adler32`` of the bytes of ``x``."""
+    import torch
+    x = _as_device_bytes(x)
+    out = torch.zeros(3, dtype=torch.int64, device=x.device)      # [result, 16 bytes of workspace]
+    with torch.cuda.device(x.device):
+        check(_lib.lib().vcfb_adler32_dev(x.data_ptr(), x.numel(), out.data_ptr(), out.data_ptr() + 8,
+                                          torch.cuda.current_stream().cuda_stream))
+    return out[:1]
+
+
+def adler32(x) -> int:
+    """``zlib.adler32(bytes of x)`` computed on the GPU."""
+    return int(adler32_dev(x).item()) & 0xFFFFFFFF
 
 
 def zlib_compress(x) -> bytes:
-    """zlib-format stream (what ``zlib.compress`` returns): ``zlib.decompress`` reads it."""
-    raw = deflate_raw(x)
-    return b"\x78\x9c" + raw + struct.pack(">I", zlib.adler32(_host_bytes(x)) & 0xFFFFFFFF)
+    """zlib-format stream (what ``zlib.compress`` returns): ``zlib.decompress`` reads it.  Deflate
+    stream and Adler-32 both come from the GPU; ``x``: numpy array or torch tensor."""
+    dev = _as_device_bytes(x)
+    dst, out_n = deflate_raw_dev(dev)
+    ad = adler32_dev(dev)
+    n = int(out_n.item())
+    return b"\x78\x9c" + dst[:n].cpu().numpy().tobytes() + struct.pack(">I", int(ad.item()) & 0xFFFFFFFF)
+
+
+def tiff_zlib(x) -> bytes:
+    """A TIFF file holding the image ``x`` -- uint8 or uint16, (H, W) or (H, W, 3), numpy array or
+    CUDA tensor -- as one strip compressed with zlib (Compression = 8, "Adobe deflate"): what
+    ``tifffile.imwrite(f, data=x, compression='zlib')`` produces in src/TIFF.py:23-31, with the
+    strip's zlib stream made on the GPU.  Baseline TIFF 6.0 + the deflate extension, little endian;
+    tifffile, libtiff (OpenCV) and Pillow read it."""
+    if _is_torch(x):
+        dtype, shape = torch_empty_numpy_dtype(x), tuple(x.shape)
+        src = x.detach().contiguous()
+    else:
+        src = np.ascontiguousarray(x)
+        dtype, shape = src.dtype, src.shape
+    if dtype not in (np.dtype(np.uint8), np.dtype(np.uint16)):
+        raise ValueError(f"tiff_zlib: uint8 or uint16 images, got {dtype}")     # the assert of src/TIFF.py:26
+    if not (len(shape) == 2 or (len(shape) == 3 and shape[2] == 3)) or 0 in shape:
+        raise ValueError(f"tiff_zlib: (H, W) or (H, W, 3) images, got shape {shape}")
+    H, W = shape[:2]
+    spp = 1 if len(shape) == 2 else 3
+    bits = 8 * dtype.itemsize
+    data = zlib_compress(src)
+    if 8 + len(data) + 512 >= 1 << 32:
+        raise ValueError("image too large for a classic TIFF")
+    pad = len(data) & 1                                    # the IFD starts on a word boundary
+    ifd_off = 8 + len(data) + pad
+    SHORT, LONG = 3, 4
+    entries = []
+
+    def entry(tag, typ, count, value):
+        entries.append(struct.pack("<HHI", tag, typ, count) + value)
+
+    n_entries = 11
+    extra_off = ifd_off + 2 + 12 * n_entries + 4
+    entry(256, LONG, 1, struct.pack("<I", W))                                  # ImageWidth
+    entry(257, LONG, 1, struct.pack("<I", H))                                  # ImageLength
+    if spp == 1:
+        entry(258, SHORT, 1, struct.pack("<HH", bits, 0))                      # BitsPerSample
+        extra = b""
+    else:
+        entry(258, SHORT, spp, struct.pack("<I", extra_off))
+        extra = struct.pack("<%dH" % spp, *([bits] * spp))
+    entry(259, SHORT, 1, struct.pack("<HH", 8, 0))                             # Compression: deflate
+    entry(262, SHORT, 1, struct.pack("<HH", 2 if spp == 3 else 1, 0))          # Photometric: RGB / min-is-black
+    entry(273, LONG, 1, struct.pack("<I", 8))                                  # StripOffsets
+    entry(277, SHORT, 1, struct.pack("<HH", spp, 0))                           # SamplesPerPixel
+    entry(278, LONG, 1, struct.pack("<I", H))                                  # RowsPerStrip
+    entry(279, LONG, 1, struct.pack("<I", len(data)))                          # StripByteCounts
+    entry(284, SHORT, 1, struct.pack("<HH", 1, 0))                             # PlanarConfiguration: chunky
+    entry(339, SHORT, 1, struct.pack("<HH", 1, 0))                             # SampleFormat: unsigned
+    assert len(entries) == n_entries
+    return (b"II*\x00" + struct.pack("<I", ifd_off) + data + b"\x00" * pad + struct.pack("<H", n_entries)
+            + b"".join(entries) + struct.pack("<I", 0) + extra)
 
 
 def _npy_header(dtype: np.dtype, shape) -> bytes:
