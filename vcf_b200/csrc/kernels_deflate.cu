@@ -68,7 +68,7 @@ struct SegShared {
   int stored;
 };
 
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 3)
 deflate_segments_kernel(const uint8_t* __restrict__ src, long long n, int piece, uint8_t* __restrict__ regions,
                         long long stride, uint32_t* __restrict__ seg_size) {
   __shared__ SegShared sh;
