@@ -158,10 +158,15 @@ def tiff_zlib(x) -> bytes:
         raise ValueError(f"tiff_zlib: uint8 or uint16 images, got {dtype}")     # the assert of src/TIFF.py:26
     if not (len(shape) == 2 or (len(shape) == 3 and shape[2] == 3)) or 0 in shape:
         raise ValueError(f"tiff_zlib: (H, W) or (H, W, 3) images, got shape {shape}")
+    return _tiff_container(dtype, shape, zlib_compress(src))
+
+
+def _tiff_container(dtype, shape, data: bytes) -> bytes:
+    """Little-endian baseline TIFF around one zlib-compressed strip ``data`` holding a C-contiguous
+    image of this dtype (uint8 / uint16) and shape ((H, W) or (H, W, 3)).  Host logic only."""
     H, W = shape[:2]
     spp = 1 if len(shape) == 2 else 3
-    bits = 8 * dtype.itemsize
-    data = zlib_compress(src)
+    bits = 8 * np.dtype(dtype).itemsize
     if 8 + len(data) + 512 >= 1 << 32:
         raise ValueError("image too large for a classic TIFF")
     pad = len(data) & 1                                    # the IFD starts on a word boundary
@@ -221,30 +226,40 @@ def _stored_block(data: bytes) -> bytes:
 def savez_compressed(file, **arrays) -> None:
     """``np.savez_compressed(file, **arrays)`` with the deflate streams produced on the GPU.
     ``file``: path or binary file object.  ``np.load`` reads the result (src/z_lib.py:25-29)."""
+    members = []
+    for name, arr in arrays.items():
+        if _is_torch(arr):
+            dtype = torch_empty_numpy_dtype(arr)
+            shape = tuple(arr.shape)
+            src = arr.detach().contiguous()
+        else:
+            src = np.ascontiguousarray(arr)
+            dtype, shape = src.dtype, src.shape
+        if dtype.hasobject:
+            raise ValueError("object arrays are not supported")
+        header = _npy_header(dtype, shape)
+        dev = _as_device_bytes(src)                    # one upload (numpy) or none (CUDA tensor)
+        dst, out_n = deflate_raw_dev(dev)
+        crc_body = crc32_dev(dev)
+        nbytes = int(out_n.item())
+        members.append((name, header, dst[:nbytes].cpu().numpy().tobytes(), int(crc_body.item()) & 0xFFFFFFFF, dev.numel()))
+    _npz_container(file, members)
+
+
+def _npz_container(file, members) -> None:
+    """The zip archive np.savez_compressed writes, from finished parts.  ``members``: (name, .npy
+    header bytes, raw deflate stream of the array's bytes, crc32 of the array's bytes, their count).
+    Host logic only."""
     own = isinstance(file, (str, bytes)) or hasattr(file, "__fspath__")
     fh = open(file, "wb") if own else file
     try:
         start = fh.tell()
         central = []
-        for name, arr in arrays.items():
-            if _is_torch(arr):
-                dtype = torch_empty_numpy_dtype(arr)
-                shape = tuple(arr.shape)
-                src = arr.detach().contiguous()
-            else:
-                src = np.ascontiguousarray(arr)
-                dtype, shape = src.dtype, src.shape
-            if dtype.hasobject:
-                raise ValueError("object arrays are not supported")
-            header = _npy_header(dtype, shape)
-            dev = _as_device_bytes(src)                    # one upload (numpy) or none (CUDA tensor)
-            dst, out_n = deflate_raw_dev(dev)
-            crc_body = crc32_dev(dev)
-            nbytes = int(out_n.item())
-            # the member's stream: the .npy header as a stored block, then the GPU's blocks
-            comp = _stored_block(header) + dst[:nbytes].cpu().numpy().tobytes()
-            crc = crc32_combine(zlib.crc32(header) & 0xFFFFFFFF, int(crc_body.item()) & 0xFFFFFFFF, dev.numel())
-            usize = len(header) + dev.numel()
+        for name, header, stream, crc_body, nbody in members:
+            # the member's stream: the .npy header as a stored block, then the array's blocks
+            comp = _stored_block(header) + stream
+            crc = crc32_combine(zlib.crc32(header) & 0xFFFFFFFF, crc_body, nbody)
+            usize = len(header) + nbody
             if usize >= 0xFFFFFFFF or len(comp) >= 0xFFFFFFFF:
                 raise ValueError("array too large for a zip member without zip64")
             fname = (name + ".npy").encode()
