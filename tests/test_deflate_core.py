@@ -136,3 +136,20 @@ def test_crc32_in_chunks_equals_zlib(emul):
                 if chunk == 1 and n > 70000:
                     continue
                 assert L.crc_emul(view.ctypes.data, n, chunk) == (zlib.crc32(view.tobytes()) & 0xFFFFFFFF), (n, lead, chunk)
+
+
+def test_full_alphabet_and_degenerate_alphabets(emul):
+    """All 286 literal/length symbols in one segment (every byte value, every match length), and
+    the smallest alphabets (one literal + end of block; one literal + one length)."""
+    rng = np.random.default_rng(13)
+    parts = []
+    for L in range(3, 259):                       # a run of L + 1 equal bytes = literal + match of length L
+        parts.append(np.full(L + 1, int(rng.integers(0, 256)), np.uint8))
+        parts.append(np.array([(int(parts[-1][0]) + 1) % 256], np.uint8))
+    parts.append(np.arange(256, dtype=np.uint8))
+    data = np.concatenate(parts)
+    _roundtrip(emul, data, piece=1 << 16, nt=1)               # one thread: the sequential parse, all lengths intact
+    _roundtrip(emul, data, piece=258, nt=512)
+    for data in (np.array([7], np.uint8), np.full(2, 7, np.uint8), np.full(259, 7, np.uint8), np.full(258 * 4 + 1, 7, np.uint8)):
+        _roundtrip(emul, data, piece=258, nt=512)
+        _roundtrip(emul, data, piece=8, nt=2)
