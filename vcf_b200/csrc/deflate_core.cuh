@@ -58,7 +58,8 @@ DFL_HD void length_symbol(int L, int* sym, int* ebits, int* eval) {
 // or segment: the decoder has produced it by then).  V::lit(byte) / V::match(length).
 // src must be 8-byte aligned.  The input is read as aligned 64-bit words kept in a register (one
 // load per 8 bytes: the pieces of a warp's threads lie `piece` bytes apart, so every load costs one
-// L1 wavefront per thread); bytes past n are never touched.
+// L1 wavefront per thread -- measured neutral against byte loads); bytes past n are
+// never touched.
 #if defined(__CUDA_ARCH__)
 #define DFL_CTZ64(x) (__ffsll((long long)(x)) - 1)
 #else
