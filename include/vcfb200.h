@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define VCFB_VERSION 120 /* 0.2.0: + vcfb_deflate_dev, vcfb_deflate_bound, vcfb_deflate_workspace, vcfb_crc32_dev, vcfb_adler32_dev (0.1.1: vcfb_launch_count, motion estimation) */
+#define VCFB_VERSION 130 /* 0.3.0: + VCFB_F_SYNTH_F32; 0.2.0: + vcfb_deflate_dev, vcfb_deflate_bound, vcfb_deflate_workspace, vcfb_crc32_dev, vcfb_adler32_dev (0.1.1: vcfb_launch_count, motion estimation) */
 
 /* error codes */
 #define VCFB_OK 0
@@ -60,6 +60,13 @@ extern "C" {
                                  the DCT.  Without it the float32 encoder is bit-exact
                                  with the reference's float32 path (:276); with it
                                  < 1e-6 of the indices may differ. */
+
+#define VCFB_F_SYNTH_F32 32u  /* decode, with VCFB_F_FP64: the upstream variant in which
+                                 DCT2D.block_DCT.synthesize_image stores its float64 result in a
+                                 float32 array (the un-vendored package cannot be read):
+                                 to_RGB, +128 and the truncation then run on float32.  Differs from
+                                 the default chain by <= 1 LSB per pixel, up to 0.03 dB on content
+                                 dominated by DC-only blocks (tests/test_oracle_variants.py). */
 
 #define VCFB_F_HIST 16u       /* statistics: also accumulate the 3 x 256 histogram of the indices
                                  (one shared-memory atomic per sample; off = only the sums) */

@@ -344,7 +344,7 @@ def encode_array(img_u8: np.ndarray, B: int = 8, q=32, *, color: str = "YCoCg",
 def decode_array(idx_u8: np.ndarray, shape, B: int = 8, q=32, *, color: str = "YCoCg",
                  perceptual: bool = False, disable_subbands: bool = False,
                  loop: bool = False, return_float: bool = False,
-                 dtype=None) -> np.ndarray:
+                 dtype=None, synth_store_dtype=None) -> np.ndarray:
     """uint8 indices (Hp,Wp,3) -> uint8 RGB (H,W,3) written at :467.
 
     The reference's dtype chain (dtype=None): int16 indices (:398), int16
@@ -353,7 +353,11 @@ def decode_array(idx_u8: np.ndarray, shape, B: int = 8, q=32, *, color: str = "Y
     dtype=np.float32 restates the same flow with a float32 IDCT (the fast
     mode of the GPU decoder is compared against the float64 chain, not this).
     return_float hands back the un-clipped float image that
-    ``CT.CoDec.filter`` receives (:461)."""
+    ``CT.CoDec.filter`` receives (:461).
+    synth_store_dtype=np.float32 is the upstream VARIANT in which
+    ``DCT2D.block_DCT.synthesize_image`` stores its (float64) result in a float32
+    array (the package is not vendored, so this cannot be ruled out; the GPU
+    exposes it as VCFB_F_SYNTH_F32, tests/test_oracle_variants.py measures it)."""
     k = idx_u8.astype(np.int16)                                  # :398
     k -= OFFSET                                                  # :402
     y = DeadzoneQuantizer(q).decode(k)                           # :410
@@ -370,6 +374,8 @@ def decode_array(idx_u8: np.ndarray, shape, B: int = 8, q=32, *, color: str = "Y
         f[..., 2] /= (Cq / 99)[None, :, None, :]
         blk[...] = f          # stored back into the (int16) array: truncates
     ct = (synthesize_image_loop if loop else synthesize_image)(coef, B, B)  # :440
+    if synth_store_dtype is not None:
+        ct = ct.astype(synth_store_dtype)
     ct = remove_padding(ct, shape)                               # :444
     if color == "YCoCg":
         y = ycocg_to_rgb(ct)                                     # :449

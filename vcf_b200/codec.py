@@ -22,7 +22,7 @@ from typing import Optional
 import numpy as np
 
 from . import _lib
-from ._lib import (COLOR_YCOCG, COLOR_YCRCB, F_CONTRACT, F_FP64, F_HIST, F_NO_SUBBANDS, F_PERCEPTUAL,
+from ._lib import (COLOR_YCOCG, COLOR_YCRCB, F_CONTRACT, F_FP64, F_HIST, F_NO_SUBBANDS, F_PERCEPTUAL, F_SYNTH_F32,
                    STAT_HIST, STAT_LEN, VcfbError, check, padded_dims)
 
 _COLORS = {"YCoCg": COLOR_YCOCG, "YCrCb": COLOR_YCRCB}
@@ -84,7 +84,7 @@ class Codec:
 
     def __init__(self, block_size: int = 8, q=32, color: str = "YCoCg", perceptual: bool = False,
                  disable_subbands: bool = False, fp64: bool = False, contract: bool = False,
-                 device: Optional[int] = None, hist: bool = True):
+                 device: Optional[int] = None, hist: bool = True, synth_f32: bool = False):
         if color not in _COLORS:
             raise ValueError(f"color must be one of {list(_COLORS)}")
         if block_size not in (4, 8, 16, 32):
@@ -97,11 +97,18 @@ class Codec:
         self.flags = ((F_PERCEPTUAL if perceptual else 0) | (F_NO_SUBBANDS if disable_subbands else 0)
                       | (F_FP64 if fp64 else 0) | (F_CONTRACT if contract else 0)
                       | (F_HIST if hist else 0))      # histogram of the indices in the statistics
+        # decode only: upstream variant "synthesize_image stores float32" (include/vcfb200.h)
+        self.synth_f32 = bool(synth_f32)
+        if synth_f32 and not fp64:
+            raise ValueError("synth_f32 is a variant of the float64 decoder (fp64=True)")
         self.fp64 = bool(fp64)
         self.device = device
         self._weights_np = perceptual_weights(self.B) if perceptual else None
         self._weights_dev = {}
         self._ctx = None
+
+    def _dec_flags(self):
+        return self.flags | (F_SYNTH_F32 if self.synth_f32 else 0)
 
     # -- plumbing ---------------------------------------------------------------
     def __del__(self):
@@ -225,7 +232,7 @@ class Codec:
             w = self._dev_weights(dev)
             with torch.cuda.device(dev):
                 stream = torch.cuda.current_stream().cuda_stream
-                check(L.vcfb_decode_dev(k.data_ptr(), n, H, W, self.B, self.q, self.color, self.flags,
+                check(L.vcfb_decode_dev(k.data_ptr(), n, H, W, self.B, self.q, self.color, self._dec_flags(),
                                         w.data_ptr() if w is not None else None,
                                         rgb.data_ptr() if rgb is not None else None,
                                         yf.data_ptr() if yf is not None else None,
@@ -254,7 +261,7 @@ class Codec:
         st = np.zeros(STAT_LEN, dtype=np.int64) if stats else None
         w = self._weights_np
         check(L.vcfb_decode_host(self._host_ctx(), k.ctypes.data, n, H, W, self.B, self.q, self.color,
-                                 self.flags, w.ctypes.data if w is not None else None,
+                                 self._dec_flags(), w.ctypes.data if w is not None else None,
                                  rgb.ctypes.data if rgb is not None else None,
                                  yf.ctypes.data if yf is not None else None,
                                  org.ctypes.data if org is not None else None,
@@ -367,5 +374,6 @@ def rd_stats(rgb, block_size=8, q=32, **kw):
         merged[4] += s["nonzero"]
         merged[5] += s["sumabs"]
         merged[6] += s["nindices"]
+        merged[7] += s["sumdiff"]
         merged[STAT_HIST:] += s["hist"].ravel()
     return stats_dict(merged)

@@ -50,7 +50,8 @@ static int check_common(const void* in, int n_frames, int H, int W, int B, doubl
   if (color != VCFB_COLOR_YCOCG && color != VCFB_COLOR_YCRCB) { set_error("unknown colour transform"); return VCFB_E_ARG; }
   if ((flags & VCFB_F_PERCEPTUAL) && !weights) { set_error("VCFB_F_PERCEPTUAL needs weights"); return VCFB_E_ARG; }
   if ((flags & VCFB_F_FP64) && (flags & VCFB_F_CONTRACT)) { set_error("VCFB_F_CONTRACT is float32 only"); return VCFB_E_ARG; }
-  if (flags & ~(VCFB_F_NO_SUBBANDS | VCFB_F_PERCEPTUAL | VCFB_F_FP64 | VCFB_F_CONTRACT | VCFB_F_HIST)) { set_error("unknown flag bits"); return VCFB_E_ARG; }
+  if ((flags & VCFB_F_SYNTH_F32) && !(flags & VCFB_F_FP64)) { set_error("VCFB_F_SYNTH_F32 is a variant of the float64 decoder: set VCFB_F_FP64 too"); return VCFB_E_ARG; }
+  if (flags & ~(VCFB_F_NO_SUBBANDS | VCFB_F_PERCEPTUAL | VCFB_F_FP64 | VCFB_F_CONTRACT | VCFB_F_HIST | VCFB_F_SYNTH_F32)) { set_error("unknown flag bits"); return VCFB_E_ARG; }
   return VCFB_OK;
 }
 
@@ -97,6 +98,7 @@ int vcfb_encode_dev(const uint8_t* rgb, int n_frames, int H, int W, int B, doubl
   int rc = check_common(rgb, n_frames, H, W, B, q, color, flags, weights, &a.g);
   if (rc) return rc;
   if (!idx_out) { set_error("idx_out is NULL"); return VCFB_E_ARG; }
+  if (flags & VCFB_F_SYNTH_F32) { set_error("VCFB_F_SYNTH_F32 is a decode flag"); return VCFB_E_ARG; }
   a.rgb = rgb;
   a.idx = idx_out;
   a.n_frames = n_frames;
@@ -138,9 +140,11 @@ int vcfb_decode_dev(const uint8_t* idx, int n_frames, int H, int W, int B, doubl
   a.flags = flags;
   a.weights = weights;
   a.stats = reinterpret_cast<unsigned long long*>(stats);
-  rc = B == 16 ? launch_decode_fast16(a, static_cast<cudaStream_t>(cuda_stream))
-               : launch_decode_fast(a, B, static_cast<cudaStream_t>(cuda_stream));
-  if (rc != VCFB_E_UNSUPP) return rc;
+  if (!(flags & VCFB_F_SYNTH_F32)) {      // the upstream-variant decoder exists in the general kernel only
+    rc = B == 16 ? launch_decode_fast16(a, static_cast<cudaStream_t>(cuda_stream))
+                 : launch_decode_fast(a, B, static_cast<cudaStream_t>(cuda_stream));
+    if (rc != VCFB_E_UNSUPP) return rc;
+  }
   return launch_decode_general(a, B, static_cast<cudaStream_t>(cuda_stream));
 }
 
@@ -268,11 +272,40 @@ static int slot_drain(Slot* sl) {
   return VCFB_OK;
 }
 
+
+// Scope guard of the host entry points: remembers the calling thread's current device, makes the
+// context's device current, and on the way out (a) on any path that did not finish cleanly waits
+// for the slot streams and forgets the pending pinned->pageable copies -- their destinations are
+// the caller's buffers of THIS call and must never be written by a later one -- and (b) restores
+// the caller's device, so a torch process sitting on cuda:N is not silently moved.
+struct HostScope {
+  vcfb_ctx* c;
+  int prev = -1;
+  bool ok = false;
+  cudaError_t err = cudaSuccess;
+  explicit HostScope(vcfb_ctx* ctx) : c(ctx) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    err = cudaSetDevice(c->device);
+  }
+  ~HostScope() {
+    if (!ok && err == cudaSuccess) {
+      for (int i = 0; i < NSLOT; ++i) {
+        if (c->slot[i].s) cudaStreamSynchronize(c->slot[i].s);
+        c->slot[i].npend = 0;
+      }
+    }
+    if (prev >= 0 && prev != c->device) cudaSetDevice(prev);
+  }
+};
+
 static size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 
 int vcfb_ctx_create(int device, vcfb_ctx** out) {
   if (!out) { set_error("out is NULL"); return VCFB_E_ARG; }
   *out = nullptr;
+  int prev = -1;
+  if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+  struct Restore { int d; ~Restore() { if (d >= 0) cudaSetDevice(d); } } restore{prev};
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
   vcfb_ctx* c = new (std::nothrow) vcfb_ctx();
@@ -291,6 +324,8 @@ int vcfb_ctx_create(int device, vcfb_ctx** out) {
 
 void vcfb_ctx_destroy(vcfb_ctx* c) {
   if (!c) return;
+  int prev = -1;
+  if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
   cudaSetDevice(c->device);
   for (int i = 0; i < NSLOT; ++i) {
     if (c->slot[i].s) { cudaStreamSynchronize(c->slot[i].s); cudaStreamDestroy(c->slot[i].s); }
@@ -299,6 +334,7 @@ void vcfb_ctx_destroy(vcfb_ctx* c) {
   }
   if (c->aux) cudaFree(c->aux);
   if (c->ready) cudaEventDestroy(c->ready);
+  if (prev >= 0 && prev != c->device) cudaSetDevice(prev);
   delete c;
 }
 
@@ -359,7 +395,8 @@ int vcfb_encode_host(vcfb_ctx* c, const uint8_t* rgb, int n_frames, int H, int W
   int rc = check_common(rgb, n_frames, H, W, B, q, color, flags, weights, &g);
   if (rc) return rc;
   if (!idx_out) { set_error("idx_out is NULL"); return VCFB_E_ARG; }
-  cudaError_t e = cudaSetDevice(c->device);
+  HostScope scope(c);
+  cudaError_t e = scope.err;
   if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
   const size_t in_f = size_t(H) * W * 3, out_f = size_t(g.Hp) * g.Wp * 3;
   const size_t w_b = (flags & VCFB_F_PERCEPTUAL) ? size_t(2) * B * B * sizeof(double) : 0;
@@ -394,7 +431,9 @@ int vcfb_encode_host(vcfb_ctx* c, const uint8_t* rgb, int n_frames, int H, int W
     }
     if (e != cudaSuccess) return cuda_fail(e, "device->host copy");
   }
-  return finish(c, d_st, stats);
+  rc = finish(c, d_st, stats);
+  scope.ok = (rc == VCFB_OK);
+  return rc;
 }
 
 int vcfb_decode_host(vcfb_ctx* c, const uint8_t* idx, int n_frames, int H, int W, int B, double q,
@@ -405,7 +444,8 @@ int vcfb_decode_host(vcfb_ctx* c, const uint8_t* idx, int n_frames, int H, int W
   int rc = check_common(idx, n_frames, H, W, B, q, color, flags, weights, &g);
   if (rc) return rc;
   if (!rgb_out && !y_out && !(original && stats)) { set_error("decode has no output"); return VCFB_E_ARG; }
-  cudaError_t e = cudaSetDevice(c->device);
+  HostScope scope(c);
+  cudaError_t e = scope.err;
   if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
   const size_t px_f = size_t(H) * W * 3, idx_f = size_t(g.Hp) * g.Wp * 3;
   const size_t y_f = y_out ? px_f * ((flags & VCFB_F_FP64) ? 8 : 4) : 0;
@@ -465,14 +505,17 @@ int vcfb_decode_host(vcfb_ctx* c, const uint8_t* idx, int n_frames, int H, int W
       if (e != cudaSuccess) return cuda_fail(e, "device->host copy");
     }
   }
-  return finish(c, d_st, stats);
+  rc = finish(c, d_st, stats);
+  scope.ok = (rc == VCFB_OK);
+  return rc;
 }
 
 int vcfb_color_encode_host(vcfb_ctx* c, const uint8_t* rgb, long long n_pixels, double q, int color,
                            uint16_t* k_out) {
   if (!c) { set_error("ctx is NULL"); return VCFB_E_ARG; }
   if (!rgb || !k_out || n_pixels <= 0) { set_error("bad argument"); return VCFB_E_ARG; }
-  cudaError_t e = cudaSetDevice(c->device);
+  HostScope scope(c);
+  cudaError_t e = scope.err;
   if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
   Slot* sl = &c->slot[0];
   int rc = slot_drain(sl);
@@ -488,6 +531,7 @@ int vcfb_color_encode_host(vcfb_ctx* c, const uint8_t* rgb, long long n_pixels, 
   e = cudaMemcpyAsync(k_out, sl->dev + o_out, out_b, cudaMemcpyDeviceToHost, sl->s);
   if (e == cudaSuccess) e = cudaStreamSynchronize(sl->s);
   if (e != cudaSuccess) return cuda_fail(e, "colour encode (device->host / synchronize)");
+  scope.ok = true;
   return VCFB_OK;
 }
 
@@ -495,7 +539,8 @@ int vcfb_color_decode_host(vcfb_ctx* c, const uint16_t* k, long long n_pixels, d
                            uint8_t* rgb_out) {
   if (!c) { set_error("ctx is NULL"); return VCFB_E_ARG; }
   if (!k || !rgb_out || n_pixels <= 0) { set_error("bad argument"); return VCFB_E_ARG; }
-  cudaError_t e = cudaSetDevice(c->device);
+  HostScope scope(c);
+  cudaError_t e = scope.err;
   if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
   Slot* sl = &c->slot[0];
   int rc = slot_drain(sl);
@@ -511,6 +556,7 @@ int vcfb_color_decode_host(vcfb_ctx* c, const uint16_t* k, long long n_pixels, d
   e = cudaMemcpyAsync(rgb_out, sl->dev + o_out, out_b, cudaMemcpyDeviceToHost, sl->s);
   if (e == cudaSuccess) e = cudaStreamSynchronize(sl->s);
   if (e != cudaSuccess) return cuda_fail(e, "colour decode (device->host / synchronize)");
+  scope.ok = true;
   return VCFB_OK;
 }
 

@@ -486,6 +486,25 @@ __global__ void __launch_bounds__(NT) decode_kernel(const DecArgs a) {
     const T c1 = F[(1 * B + r) * FP + x];
     const T c2 = F[(2 * B + r) * FP + x];
     T R, G, Bv;
+    if (sizeof(T) == 8 && (a.flags & VCFB_F_SYNTH_F32)) {
+      // upstream variant: synthesize_image stores its float64 result in a float32 array, so the
+      // colour transform, the +128 and the truncation run on float32 (tests/test_oracle_variants.py)
+      using OF = Ops<float, true>;
+      const float f0 = float(c0), f1 = float(c1), f2 = float(c2);
+      float Rf, Gf, Bf;
+      if (a.color == VCFB_COLOR_YCOCG) {
+        Rf = OF::sub(OF::add(f0, f1), f2);
+        Gf = OF::add(f0, f2);
+        Bf = OF::sub(OF::sub(f0, f1), f2);
+      } else {
+        Rf = OF::add(f0, OF::mul(f1, 1.403f));
+        Gf = OF::add(OF::add(f0, OF::mul(f1, -0.714f)), OF::mul(f2, -0.344f));
+        Bf = OF::add(f0, OF::mul(f2, 1.773f));
+      }
+      R = T(OF::add(Rf, 128.0f));
+      G = T(OF::add(Gf, 128.0f));
+      Bv = T(OF::add(Bf, 128.0f));
+    } else {
     if (a.color == VCFB_COLOR_YCOCG) {   // Y + Co - Cg ; Y + Cg ; Y - Co - Cg, left to right
       R = O::sub(O::add(c0, c1), c2);
       G = O::add(c0, c2);
@@ -498,6 +517,7 @@ __global__ void __launch_bounds__(NT) decode_kernel(const DecArgs a) {
     R = O::add(R, T(128));
     G = O::add(G, T(128));
     Bv = O::add(Bv, T(128));
+    }
     if (a.y_out) {
       T* yo = reinterpret_cast<T*>(a.y_out) + ((size_t(f) * g.H + gy) * g.W + gx) * 3;
       yo[0] = R; yo[1] = G; yo[2] = Bv;

@@ -277,3 +277,48 @@ def _npz_container(file, members) -> None:
     finally:
         if own:
             fh.close()
+
+
+_CS_STREAMS = {}
+
+
+def encode_to_codestream(codec, rgb, n_streams: int = 3):
+    """Host RGB frames -> per-frame raw deflate code-streams, with everything between on the GPU.
+
+    ``codec``: a :class:`vcf_b200.Codec`; ``rgb``: numpy uint8 (n,H,W,3), ideally in pinned memory
+    (``vcf_b200.pinned_empty`` / a pinned torch tensor's ``.numpy()``).  Frame f is uploaded,
+    transformed (src/2D-DCT.py:276-361) and deflated (the zlib call of src/z_lib.py:19-23 /
+    src/TIFF.py:23-31) on CUDA stream f mod ``n_streams``, so uploads overlap kernels; only the
+    code-streams cross PCIe on the way back (3 B/pixel up, ~0.1 B/pixel down instead of 3 + 3).
+    Returns a list of ``bytes``, one complete deflate stream per frame
+    (``zlib.decompress(s, -15)`` gives the frame's uint8 index array)."""
+    import torch
+    if not torch.cuda.is_available():
+        raise _lib.VcfbError("no CUDA device: vcf_b200 has no CPU fallback")
+    if rgb.ndim == 3:
+        rgb = rgb[None]
+    dev = torch.device("cuda", int(codec.device) if codec.device is not None else torch.cuda.current_device())
+    key = (dev.index, n_streams)
+    if key not in _CS_STREAMS:
+        with torch.cuda.device(dev):
+            _CS_STREAMS[key] = [torch.cuda.Stream() for _ in range(n_streams)]
+    streams = _CS_STREAMS[key]
+    cur = torch.cuda.current_stream(dev)
+    pend = []
+    with torch.cuda.device(dev):
+        for st in streams:
+            st.wait_stream(cur)
+        for f in range(rgb.shape[0]):
+            st = streams[f % n_streams]
+            with torch.cuda.stream(st):
+                xd = torch.from_numpy(rgb[f]).to(dev, non_blocking=True)
+                k = codec.encode(xd)
+                dst, nb = deflate_raw_dev(k)
+                pend.append((dst, nb))
+        for st in streams:
+            st.synchronize()
+        lens = torch.cat([nb for _, nb in pend]).cpu().tolist()
+        out = []
+        for (dst, _), n in zip(pend, lens):
+            out.append(dst[:int(n)].cpu().numpy().tobytes())
+    return out

@@ -51,6 +51,8 @@ for _p in (parser.parser_encode, parser.parser_decode):
 parser.parser_encode.add_argument("-L", "--Lambda", type=parser.int_or_str, help="when given (float): pick the block size in {4, 8, 16, 32} minimising bytes + Lambda * RMSE")
 parser.parser_decode.add_argument("--b200_fast_decode", action='store_true', help="float32 GPU decoder (pixels within +-1 of the reference, PSNR within 0.01 dB) instead of the bit-exact float64 one", default=False)
 
+parser.parser_decode.add_argument("--b200_synth_f32", action='store_true', help="float64 GPU decoder in the upstream variant that stores the synthesised image as float32 (see include/vcfb200.h VCFB_F_SYNTH_F32)", default=False)
+
 args = parser.parser.parse_known_args()[0]
 CT = importlib.import_module(args.color_transform)
 
@@ -85,12 +87,14 @@ class CoDec(CT.CoDec):
         if B not in SUPPORTED_B:
             raise ValueError(f"block size {B} is not supported by the GPU path (supported: {SUPPORTED_B})")
         fp64 = decode and not getattr(self.args, "b200_fast_decode", False)
-        key = (B, fp64)
+        synth32 = fp64 and bool(getattr(self.args, "b200_synth_f32", False))
+        key = (B, fp64, synth32)
         if key not in self._codecs:
             # ``-t`` only selects the base class in the reference; the arithmetic is
             # always YCoCg (src/2D-DCT.py:22-23, :298, :449).
             self._codecs[key] = Codec(block_size=B, q=self.QSS, color="YCoCg", perceptual=self.perceptual,
-                                      disable_subbands=self.disable_subbands, fp64=fp64)
+                                      disable_subbands=self.disable_subbands, fp64=fp64, synth_f32=synth32,
+                                      device=getattr(self, "device", None))
         return self._codecs[key]
 
     @staticmethod

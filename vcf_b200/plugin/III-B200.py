@@ -51,14 +51,37 @@ def _rank_world():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
 
+def _local_device():
+    """One process per GPU under torchrun: rank r of a node works on GPU LOCAL_RANK."""
+    import torch
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if torch.cuda.is_available():
+        local %= max(1, torch.cuda.device_count())
+        torch.cuda.set_device(local)
+    return local
+
+
+def _wait_for(paths, timeout_s=600.0, poll_s=0.05):
+    """Ranks other than 0 wait until rank 0 has written the extracted frames (a marker file
+    written after the last frame closes the race with a half-written PNG)."""
+    import time
+    t0 = time.time()
+    while not all(os.path.exists(p) for p in paths):
+        if time.time() - t0 > timeout_s:
+            raise TimeoutError(f"frames not extracted after {timeout_s:.0f} s: {paths[-1]}")
+        time.sleep(poll_s)
+
+
 class CoDec:
 
     def __init__(self, args):
         logging.debug("trace")
         self.args = args
+        self.device = _local_device()
         self.transform_codec = transform.CoDec(args)
         if not hasattr(self.transform_codec, "_codec"):
             raise TypeError("III-B200 batches through the GPU transform; use -T 2D-DCT-B200")
+        self.transform_codec.device = self.device       # Codec objects of the transform stage use this GPU
         logging.info(f"Using {args.transform} codec")
 
     def bye(self):
@@ -84,7 +107,16 @@ class CoDec:
         tc = self.transform_codec
         n = int(self.args.number_of_frames)
         rank, world = _rank_world()
-        if rank == 0:
+        if world > 1:
+            # only rank 0 extracts; the others wait for a marker that is unique to this launch
+            run = os.environ.get("TORCHELASTIC_RUN_ID", "") + "." + os.environ.get("MASTER_PORT", "")
+            marker = f"{ORIGINAL_PREFIX}.extracted.{run}.{n}"
+            if rank == 0:
+                self._extract_frames(n)
+                open(marker, "w").close()
+            else:
+                _wait_for([marker])
+        else:
             self._extract_frames(n)
         lo, hi = frame_range(n, rank, world)
         if hi == lo:
