@@ -58,6 +58,8 @@ int launch_decode_general(const DecArgs& a, int B, cudaStream_t s);
 // fast path (kernels_fast.cu): VCFB_E_UNSUPP means "not covered, use the general kernel"
 int launch_encode_fast(const EncArgs& a, int B, cudaStream_t s);
 int launch_decode_fast(const DecArgs& a, int B, cudaStream_t s);
+// tensor-core tier of the B = 8 fast path, float32 fast mode (kernels_tc.cu)
+int launch_decode_tc(const DecArgs& a, cudaStream_t s);
 // B = 16 fast path (kernels_b16.cu)
 int launch_encode_fast16(const EncArgs& a, cudaStream_t s);
 int launch_decode_fast16(const DecArgs& a, cudaStream_t s);

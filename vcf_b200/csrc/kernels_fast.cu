@@ -1085,6 +1085,11 @@ int launch_decode_fast(const DecArgs& a, int B, cudaStream_t s) {
   // (kernels_dec32.cu).  Development knob VCFB_DEC32_CFG: 9x1 / 9x2 = the pocketfft codelets in
   // float32 (individually rounded / contracted), other values = launch shapes of the fast kernel.
   const int cfg32 = dev_cfg("VCFB_DEC32_CFG");
+  static const bool use_tc = getenv("VCFB_TC") != nullptr;
+  if (use_tc && cfg32 == 0) {
+    const int rc = launch_decode_tc(a, s);
+    if (rc != VCFB_E_UNSUPP) return rc;
+  }
   if (cfg32 == 91) return launch_dec_t<float, true, 4, 2>(in_map, out_map, fa, s);
   if (cfg32 == 92) return launch_dec_t<float, false, 4, 2>(in_map, out_map, fa, s);
   return launch_decode_f32a(cfg32, in_map, out_map, fa, s);

@@ -1,0 +1,109 @@
+// tcgen05 / tensor-memory wrappers (inline PTX, sm_100a) for the tensor-core tier of the B=8
+// transform.  Descriptor layouts follow cute/arch/mma_sm100_desc.hpp (InstrDescriptor,
+// SmemDescriptor) and cute/atom/mma_traits_sm100.hpp (canonical no-swizzle layouts); they were
+// checked on the hardware with profiles/microbench/tc_bringup.cu before anything was built on them.
+#pragma once
+
+#include <stdint.h>
+
+#include "tma.cuh"
+
+namespace vcfb {
+namespace tc {
+
+// ---- mbarrier pieces not in tma.cuh -------------------------------------------------------
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tma::smem_u32(bar)) : "memory");
+}
+// spin on try_wait (unique labels per expansion through %=)
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "TCW_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra TCW_%=;\n\t"
+      "}" ::"r"(tma::smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// ---- tensor memory ------------------------------------------------------------------------
+// One warp allocates NCOLS (power of two >= 32) columns; the base address lands in shared memory.
+template <int NCOLS> __device__ __forceinline__ void tmem_alloc(uint32_t* holder) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tma::smem_u32(holder)), "n"(NCOLS)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS> __device__ __forceinline__ void tmem_dealloc(uint32_t base) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "n"(NCOLS) : "memory");
+}
+__device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// lane i of the warp <-> TMEM lane 32 * (warp % 4) + i; 8 consecutive 32-bit columns
+__device__ __forceinline__ void ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]),
+               "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
+// ---- descriptors --------------------------------------------------------------------------
+// Shared-memory matrix descriptor, no swizzle.  K-major operand of 16-bit elements:
+//   byte offset(mn, k) = (mn % 8) * 16 + (mn / 8) * SBO + (k / 8) * LBO + (k % 8) * 2
+__host__ __device__ inline int off_kmajor16(int mn, int k, int sbo, int lbo) {
+  return (mn % 8) * 16 + (mn / 8) * sbo + (k / 8) * lbo + (k % 8) * 2;
+}
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, int lbo, int sbo) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (uint64_t)((lbo >> 4) & 0x3FFF) << 16 | (uint64_t)((sbo >> 4) & 0x3FFF) << 32 |
+         (uint64_t)1 << 46;          // version 1 (Blackwell), base offset 0, layout type 0 (no swizzle)
+}
+// kind::f16 instruction descriptor: D = F32, A = B = F16, both K-major, shape M x N (K = 16)
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
+  return (1u << 4) | (uint32_t(N >> 3) << 17) | (uint32_t(M >> 4) << 24);
+}
+
+// D[tmem] (+)= A[tmem] * B[smem]^T, issued by ONE thread
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// the mbarrier receives one arrival when every MMA issued so far by this thread has completed
+// (implies tcgen05.fence::before_thread_sync)
+__device__ __forceinline__ void commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tma::smem_u32(bar))
+               : "memory");
+}
+
+// named barrier among a subset of the CTA's warps
+__device__ __forceinline__ void bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+}  // namespace tc
+}  // namespace vcfb
