@@ -79,7 +79,7 @@ bringup(const uint16_t* __restrict__ Ag, const uint16_t* __restrict__ Bg, float*
   const uint32_t a_tmem = tbase + 64;          // columns [64, 96): A, two fp16 per column
   const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
 
-  if (variant == 2) {
+  if (variant == 2 || variant == 3) {
     // thread = row of A: 64 fp16 = 32 packed words
     uint32_t w[32];
 #pragma unroll
@@ -106,7 +106,7 @@ bringup(const uint16_t* __restrict__ Ag, const uint16_t* __restrict__ Bg, float*
     for (int ks = 0; ks < K / 16; ++ks) {
       const uint64_t bdesc = make_desc(smem_u32(Bs) + ks * 2 * B_LBO, B_LBO, B_SBO);
       const uint32_t acc = ks > 0;
-      if (variant == 2) {
+      if (variant == 2 || variant == 3) {
         asm volatile(
             "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
             "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
@@ -148,7 +148,81 @@ bringup(const uint16_t* __restrict__ Ag, const uint16_t* __restrict__ Bg, float*
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tbase) : "memory");
 }
 
+
+// ---- issue / execution rate of back-to-back MMAs (argv[1] = 100 + variant, argv[2] = N) ---------------
+__global__ void __launch_bounds__(128, 1) mma_rate(int variant, int n_dim, int reps, long long* cycles) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* As = smem;
+  unsigned char* Bs = smem + 16384;            // up to 256 rows x 64 k x 2 B = 32 KB
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + 16384 + 32768);
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(smem + 16384 + 32768 + 8);
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (16384 + 32768) / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;   // fp16 ones
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(tmem_holder)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tbase = *tmem_holder;
+  if (tid == 0) {
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(n_dim >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+    const int b_lbo = n_dim / 8 * 128;
+    uint64_t bdesc[4], adesc[4];
+    for (int ks = 0; ks < 4; ++ks) {
+      bdesc[ks] = make_desc(smem_u32(Bs) + ks * 2 * b_lbo, b_lbo, 128);
+      adesc[ks] = make_desc(smem_u32(As) + ks * 2 * 2048, 2048, 128);
+    }
+    const long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        if (variant == 2)
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tbase),
+                       "r"(tbase + 256 + 8 * ks), "l"(bdesc[ks]), "r"(idesc), "r"(1u) : "memory");
+        else
+          asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tbase),
+                       "l"(adesc[ks]), "l"(bdesc[ks]), "r"(idesc), "r"(1u) : "memory");
+      }
+    }
+    const long long t1 = clock64();
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile("{\n\t.reg .pred p;\n\tW2:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t@p bra D2;\n\tbra W2;\n\tD2:\n\t}" ::"r"(smem_u32(bar)) : "memory");
+    const long long t2 = clock64();
+    cycles[0] = t1 - t0;
+    cycles[1] = t2 - t0;
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tbase) : "memory");
+}
+
+int rate_main(int variant, int n_dim) {
+  long long* dC;
+  CK(cudaMalloc(&dC, 16));
+  const int smem_bytes = 16384 + 32768 + 64;
+  CK(cudaFuncSetAttribute(mma_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  const int reps = 500;
+  for (int it = 0; it < 2; ++it) {
+    mma_rate<<<1, 128, smem_bytes>>>(variant, n_dim, reps, dC);
+    CK(cudaGetLastError());
+    CK(cudaDeviceSynchronize());
+  }
+  long long cyc[2];
+  CK(cudaMemcpy(cyc, dC, 16, cudaMemcpyDeviceToHost));
+  printf("rate: A %s, M 128 N %d K 16: %d MMAs, issue %.1f cycles each, issue + drain %.1f cycles each\n",
+         variant == 2 ? "in TMEM" : "in smem", n_dim, reps * 4, double(cyc[0]) / (reps * 4), double(cyc[1]) / (reps * 4));
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  if (argc > 1 && atoi(argv[1]) >= 100) return rate_main(atoi(argv[1]) - 100, argc > 2 ? atoi(argv[2]) : 64);
   const int arg = argc > 1 ? atoi(argv[1]) : 0;
   const int variant = arg % 10, b_bf16 = arg >= 10;
   std::vector<uint16_t> A(M * K), B(N * K);
@@ -159,6 +233,10 @@ int main(int argc, char** argv) {
     Af[i] = (float)v;
     __half h = __float2half((float)v);
     A[i] = *reinterpret_cast<uint16_t*>(&h);
+    if (variant == 3) {                 // fp16 subnormal with the bits of the byte: (v + 128) * 2^-24
+      A[i] = (uint16_t)(v + 128);
+      Af[i] = (float)(v + 128);         // compared after scaling D by 2^24
+    }
   }
   for (int n = 0; n < N; ++n)
     for (int k = 0; k < K; ++k) {
@@ -201,7 +279,7 @@ int main(int argc, char** argv) {
     for (int n = 0; n < N; ++n) {
       double ref = 0;
       for (int k = 0; k < K; ++k) ref += (double)Af[m * K + k] * Bf[n * K + k];
-      const double e = fabs(ref - D[m * N + n]);
+      const double e = fabs(ref - (variant == 3 ? 16777216.0 * D[m * N + n] : D[m * N + n]));
       if (!(e < 1e-2)) ++bad;
       if (e > maxerr || e != e) maxerr = e;
       if (fabs(ref) > maxref) maxref = fabs(ref);

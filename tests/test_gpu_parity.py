@@ -372,7 +372,7 @@ def test_fast_decode_path(q, torch_cuda):
         assert np.array_equal(got.cpu().numpy(), ref), (H, W, q, int((got.cpu().numpy() != ref).sum()))
         for contract in (False, True):
             g32 = _codec(block_size=8, q=q, contract=contract).decode(t.from_numpy(idx).cuda(), (H, W))
-            assert _lib.last_kernel() == want
+            assert _lib.last_kernel() == ("dec8_tc" if want == "dec8_fast" else want)     # float32 = the tensor-core tier
             assert np.abs(g32.cpu().numpy().astype(np.int16) - ref.astype(np.int16)).max() <= 1
     # q too large for the fast path -> general kernel (int16 wrap semantics), still exact
     img = O.synthetic_frame(16, 128, 7, "natural")
@@ -481,12 +481,18 @@ def test_float64_decoders_agree_full_size(torch_cuda, monkeypatch):
         monkeypatch.delenv("VCFB_DEC_CFG", raising=False)
 
 
-def test_fast_mode_float32_decoder_tolerances(torch_cuda):
+@pytest.mark.parametrize("tier", ["tensor_core", "cuda_core"])
+def test_fast_mode_float32_decoder_tolerances(tier, torch_cuda, monkeypatch):
     """BASELINE north star, fast mode: decoded pixels within +-1 LSB of the reference and PSNR
     matching to 0.01 dB -- natural, noise and smooth content, dense to DC-only indices, plus
-    arbitrary (non-encoder) index arrays.  (kernels_dec32.cu: scaled AAN transform in float32;
-    blocks without AC indices go through the reference's float64 chain.)"""
+    arbitrary (non-encoder) index arrays.  Both float32 decoders: the tensor-core tier
+    (kernels_tc.cu: 64 x 64 Kronecker inverse DCT on tcgen05, the default) and the CUDA-core kernel
+    (kernels_dec32.cu: scaled AAN transform); in both, blocks without AC indices go through the
+    reference's float64 chain."""
     from vcf_b200 import _lib
+    if tier == "cuda_core":
+        monkeypatch.setenv("VCFB_DEC32_CFG", "4x3")
+    expect_kernel = "dec8_tc" if tier == "tensor_core" else "dec8_fast"
     t = torch_cuda
     H, W = 1080, 1920
     yy, xx = np.mgrid[0:H, 0:W]
@@ -498,7 +504,7 @@ def test_fast_mode_float32_decoder_tolerances(torch_cuda):
             idx = O.encode_array(img, 8, q)
             ref = O.decode_array(idx, img.shape, 8, q)
             got = _codec(block_size=8, q=q).decode(t.from_numpy(idx).cuda(), (H, W)).cpu().numpy()
-            assert _lib.last_kernel() == "dec8_fast"
+            assert _lib.last_kernel() == expect_kernel
             d = np.abs(got.astype(np.int16) - ref.astype(np.int16))
             assert d.max() <= 1, (name, q, int(d.max()))
             p_ref, p_got = O.psnr(img, ref), O.psnr(img, got)

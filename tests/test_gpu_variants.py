@@ -30,8 +30,8 @@ def test_synth_f32_variant_bit_exact(B):
             assert np.abs(ref.astype(np.int16) - base.astype(np.int16)).max() <= 1
     with pytest.raises(ValueError):
         _codec(block_size=8, q=8, synth_f32=True)
-    with pytest.raises(VcfbError):
-        c = _codec(block_size=8, q=8, fp64=True, synth_f32=True)
+    with pytest.raises(VcfbError):           # the C ABI refuses the flag without VCFB_F_FP64
+        c = _codec(block_size=B, q=12, fp64=True, synth_f32=True)
         c.flags &= ~4
         c.decode(idx, (H, W))
 
@@ -61,9 +61,14 @@ def test_full_size_4k_noise_every_decoder(q, monkeypatch):
         bad = int((dec.cpu().numpy() != refd).sum())
         assert bad == 0, (q, cfg, bad)
     monkeypatch.delenv("VCFB_DEC_CFG", raising=False)
-    d32 = _codec(block_size=8, q=q).decode(got, (H, W)).cpu().numpy()
-    assert np.abs(d32.astype(np.int16) - refd.astype(np.int16)).max() <= 1
-    assert abs(O.psnr(img, d32) - O.psnr(img, refd)) < 0.01
+    for cfg32, kern in ((None, "dec8_tc"), ("4x3", "dec8_fast")):          # tensor-core tier, CUDA-core kernel
+        if cfg32:
+            monkeypatch.setenv("VCFB_DEC32_CFG", cfg32)
+        d32 = _codec(block_size=8, q=q).decode(got, (H, W)).cpu().numpy()
+        assert _lib.last_kernel() == kern
+        assert np.abs(d32.astype(np.int16) - refd.astype(np.int16)).max() <= 1
+        assert abs(O.psnr(img, d32) - O.psnr(img, refd)) < 0.01
+    monkeypatch.delenv("VCFB_DEC32_CFG", raising=False)
 
 
 def test_full_size_8k_noise_b16():

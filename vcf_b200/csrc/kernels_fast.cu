@@ -1085,7 +1085,8 @@ int launch_decode_fast(const DecArgs& a, int B, cudaStream_t s) {
   // (kernels_dec32.cu).  Development knob VCFB_DEC32_CFG: 9x1 / 9x2 = the pocketfft codelets in
   // float32 (individually rounded / contracted), other values = launch shapes of the fast kernel.
   const int cfg32 = dev_cfg("VCFB_DEC32_CFG");
-  static const bool use_tc = getenv("VCFB_TC") != nullptr;
+  // default: the tensor-core tier (kernels_tc.cu); VCFB_TC=0 or any VCFB_DEC32_CFG selects the CUDA-core kernels
+  static const bool use_tc = !(getenv("VCFB_TC") && getenv("VCFB_TC")[0] == '0');
   if (use_tc && cfg32 == 0) {
     const int rc = launch_decode_tc(a, s);
     if (rc != VCFB_E_UNSUPP) return rc;

@@ -15,17 +15,35 @@ namespace tc {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tma::smem_u32(bar)) : "memory");
 }
-// spin on try_wait (unique labels per expansion through %=)
+// Wait for the phase with this parity.  try_wait suspends the warp in hardware for up to the hinted time
+// instead of spinning: a polling warp takes issue slots from the warps that do the work (ncu on the first
+// version of kernels_tc.cu: 83 % of the issue slots busy, half of them in wait loops).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "TCW_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@!p bra TCW_%=;\n\t"
       "}" ::"r"(tma::smem_u32(bar)),
-      "r"(parity)
+      "r"(parity), "r"(200000u)
       : "memory");
+}
+// for the latency-insensitive control warps: back off between polls
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(tma::smem_u32(bar)), "r"(parity), "r"(200000u)
+        : "memory");
+    if (!done) __nanosleep(ns);
+  } while (!done);
 }
 
 // ---- tensor memory ------------------------------------------------------------------------
@@ -98,6 +116,20 @@ __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t adesc, uint64_t
 __device__ __forceinline__ void commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(tma::smem_u32(bar))
                : "memory");
+}
+
+// one lane of a converged warp (elect.sync): the tcgen05.mma operands live in uniform registers, and code the
+// compiler knows to run on a single elected lane needs no per-instruction uniformity loop
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // named barrier among a subset of the CTA's warps
