@@ -68,6 +68,14 @@ extern "C" {
                                  the default chain by <= 1 LSB per pixel, up to 0.03 dB on content
                                  dominated by DC-only blocks (tests/test_oracle_variants.py). */
 
+#define VCFB_F_FAST 64u       /* encode: the north star's fast mode -- the tensor-core encoder
+                                 (csrc/kernels_tc.cu: 64 x 64 Kronecker DCT on tcgen05, the four
+                                 rational coefficients by pocketfft's own float32 sequence): fewer
+                                 than 1e-6 of the indices differ from the reference's float32 path,
+                                 only at rounding boundaries.  Applies to B = 8, YCoCg, subbands,
+                                 q = 2^k >= 8; any other request is served by the bit-exact encoder.
+                                 Decode: ignored (float32 decode IS the fast mode). */
+
 #define VCFB_F_HIST 16u       /* statistics: also accumulate the 3 x 256 histogram of the indices
                                  (one shared-memory atomic per sample; off = only the sums) */
 

@@ -22,7 +22,7 @@ from typing import Optional
 import numpy as np
 
 from . import _lib
-from ._lib import (COLOR_YCOCG, COLOR_YCRCB, F_CONTRACT, F_FP64, F_HIST, F_NO_SUBBANDS, F_PERCEPTUAL, F_SYNTH_F32,
+from ._lib import (COLOR_YCOCG, COLOR_YCRCB, F_CONTRACT, F_FP64, F_HIST, F_NO_SUBBANDS, F_PERCEPTUAL, F_FAST, F_SYNTH_F32,
                    STAT_HIST, STAT_LEN, VcfbError, check, padded_dims)
 
 _COLORS = {"YCoCg": COLOR_YCOCG, "YCrCb": COLOR_YCRCB}
@@ -84,7 +84,7 @@ class Codec:
 
     def __init__(self, block_size: int = 8, q=32, color: str = "YCoCg", perceptual: bool = False,
                  disable_subbands: bool = False, fp64: bool = False, contract: bool = False,
-                 device: Optional[int] = None, hist: bool = True, synth_f32: bool = False):
+                 device: Optional[int] = None, hist: bool = True, synth_f32: bool = False, fast: bool = False):
         if color not in _COLORS:
             raise ValueError(f"color must be one of {list(_COLORS)}")
         if block_size not in (4, 8, 16, 32):
@@ -96,7 +96,8 @@ class Codec:
         self.color = _COLORS[color]
         self.flags = ((F_PERCEPTUAL if perceptual else 0) | (F_NO_SUBBANDS if disable_subbands else 0)
                       | (F_FP64 if fp64 else 0) | (F_CONTRACT if contract else 0)
-                      | (F_HIST if hist else 0))      # histogram of the indices in the statistics
+                      | (F_HIST if hist else 0)       # histogram of the indices in the statistics
+                      | (F_FAST if fast else 0))      # encode: tensor-core fast mode (< 1e-6 of the indices differ)
         # decode only: upstream variant "synthesize_image stores float32" (include/vcfb200.h)
         self.synth_f32 = bool(synth_f32)
         if synth_f32 and not fp64:

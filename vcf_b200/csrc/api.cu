@@ -51,7 +51,7 @@ static int check_common(const void* in, int n_frames, int H, int W, int B, doubl
   if ((flags & VCFB_F_PERCEPTUAL) && !weights) { set_error("VCFB_F_PERCEPTUAL needs weights"); return VCFB_E_ARG; }
   if ((flags & VCFB_F_FP64) && (flags & VCFB_F_CONTRACT)) { set_error("VCFB_F_CONTRACT is float32 only"); return VCFB_E_ARG; }
   if ((flags & VCFB_F_SYNTH_F32) && !(flags & VCFB_F_FP64)) { set_error("VCFB_F_SYNTH_F32 is a variant of the float64 decoder: set VCFB_F_FP64 too"); return VCFB_E_ARG; }
-  if (flags & ~(VCFB_F_NO_SUBBANDS | VCFB_F_PERCEPTUAL | VCFB_F_FP64 | VCFB_F_CONTRACT | VCFB_F_HIST | VCFB_F_SYNTH_F32)) { set_error("unknown flag bits"); return VCFB_E_ARG; }
+  if (flags & ~(VCFB_F_NO_SUBBANDS | VCFB_F_PERCEPTUAL | VCFB_F_FP64 | VCFB_F_CONTRACT | VCFB_F_HIST | VCFB_F_SYNTH_F32 | VCFB_F_FAST)) { set_error("unknown flag bits"); return VCFB_E_ARG; }
   return VCFB_OK;
 }
 
@@ -110,6 +110,17 @@ int vcfb_encode_dev(const uint8_t* rgb, int n_frames, int H, int W, int B, doubl
   a.flags = flags;
   a.weights = weights;
   a.stats = reinterpret_cast<unsigned long long*>(stats);
+  if ((flags & VCFB_F_FAST) && B == 8 && !(flags & VCFB_F_FP64)) {
+    // fast mode: tensor-core encoder; statistics, when asked for, by the streaming pass over the indices
+    static const bool tc_off = getenv("VCFB_TC") && getenv("VCFB_TC")[0] == '0';
+    if (!tc_off) {
+      rc = launch_encode_tc(a, static_cast<cudaStream_t>(cuda_stream));
+      if (rc == VCFB_OK && a.stats)
+        rc = launch_index_stats(a.idx, (long long)n_frames * a.g.Hp * a.g.Wp * 3, (flags & VCFB_F_HIST) != 0, a.stats,
+                                static_cast<cudaStream_t>(cuda_stream));
+      if (rc != VCFB_E_UNSUPP) return rc;
+    }
+  }
   rc = B == 16 ? launch_encode_fast16(a, static_cast<cudaStream_t>(cuda_stream))
                : launch_encode_fast(a, B, static_cast<cudaStream_t>(cuda_stream));
   if (rc != VCFB_E_UNSUPP) return rc;

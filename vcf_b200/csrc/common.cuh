@@ -60,6 +60,7 @@ int launch_encode_fast(const EncArgs& a, int B, cudaStream_t s);
 int launch_decode_fast(const DecArgs& a, int B, cudaStream_t s);
 // tensor-core tier of the B = 8 fast path, float32 fast mode (kernels_tc.cu)
 int launch_decode_tc(const DecArgs& a, cudaStream_t s);
+int launch_encode_tc(const EncArgs& a, cudaStream_t s);     // fast-mode encoder (VCFB_F_FAST)
 // B = 16 fast path (kernels_b16.cu)
 int launch_encode_fast16(const EncArgs& a, cudaStream_t s);
 int launch_decode_fast16(const DecArgs& a, cudaStream_t s);

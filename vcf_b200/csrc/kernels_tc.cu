@@ -653,23 +653,50 @@ std::vector<unsigned char> build_idct_limbs() {
   return t;
 }
 
-const unsigned char* device_idct_limbs() {
+// forward tables: hi limb 80 rows (64 coefficients kk = 8u + v of 4096 * DCT (x) DCT over the samples n = 8r + x,
+// then S0[x] = sum_r p[r][x] and S4[x] = (p0 + p7 + p3 + p4) - (p1 + p2 + p5 + p6) of column x), lo limb 64 rows
+std::vector<unsigned char> build_fdct_limbs() {
+  std::vector<unsigned char> t(enc::HI_BYTES + enc::LO_BYTES, 0);
+  const double PI = 3.14159265358979323846;
+  auto put = [&](int off, float v) {
+    const __half h = __float2half_rn(v);
+    *reinterpret_cast<unsigned short*>(&t[off]) = *reinterpret_cast<const unsigned short*>(&h);
+  };
+  for (int kk = 0; kk < 64; ++kk)
+    for (int n = 0; n < 64; ++n) {
+      const int u = kk / 8, v = kk % 8, r = n / 8, x = n % 8;
+      const double au = u ? 0.5 : sqrt(0.125), av = v ? 0.5 : sqrt(0.125);
+      const double val = double(1 << SCALE_LOG2) * au * av * cos((2 * r + 1) * u * PI / 16) * cos((2 * x + 1) * v * PI / 16);
+      const __half h = __float2half_rn(float(val));
+      put(tc::off_kmajor16(kk, n, 128, enc::HI_LBO), __half2float(h));
+      put(enc::HI_BYTES + tc::off_kmajor16(kk, n, 128, enc::LO_LBO), float(val - double(__half2float(h))));
+    }
+  for (int x = 0; x < 8; ++x)
+    for (int r = 0; r < 8; ++r) {
+      const bool plus = (r == 0 || r == 7 || r == 3 || r == 4);
+      put(tc::off_kmajor16(64 + x, 8 * r + x, 128, enc::HI_LBO), 1.0f);
+      put(tc::off_kmajor16(72 + x, 8 * r + x, 128, enc::HI_LBO), plus ? 1.0f : -1.0f);
+    }
+  return t;
+}
+
+const unsigned char* device_table(int which) {
   static std::mutex mu;
-  static unsigned char* tab[64] = {nullptr};
+  static unsigned char* tab[2][64] = {{nullptr}};
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
   std::lock_guard<std::mutex> lock(mu);
-  if (!tab[dev]) {
-    const std::vector<unsigned char> h = build_idct_limbs();
+  if (!tab[which][dev]) {
+    const std::vector<unsigned char> h = which ? build_fdct_limbs() : build_idct_limbs();
     unsigned char* d = nullptr;
     if (cudaMalloc(reinterpret_cast<void**>(&d), h.size()) != cudaSuccess) return nullptr;
     if (cudaMemcpy(d, h.data(), h.size(), cudaMemcpyHostToDevice) != cudaSuccess) {
       cudaFree(d);
       return nullptr;
     }
-    tab[dev] = d;
+    tab[which][dev] = d;
   }
-  return tab[dev];
+  return tab[which][dev];
 }
 
 }  // namespace
@@ -680,7 +707,7 @@ int launch_decode_tc(const DecArgs& a, cudaStream_t s) {
   if (g.W % 16 != 0 || g.nx % 16 != 0 || g.left != 0 || g.top != 0) return VCFB_E_UNSUPP;
   if ((reinterpret_cast<uintptr_t>(a.rgb) & 15) || (reinterpret_cast<uintptr_t>(a.idx) & 15)) return VCFB_E_UNSUPP;
   if (a.q_int < 1 || a.q_int > 255 || tma::encode_tiled_fn() == nullptr) return VCFB_E_UNSUPP;
-  const unsigned char* btab = device_idct_limbs();
+  const unsigned char* btab = device_table(0);
   if (!btab) return VCFB_E_UNSUPP;
   CUtensorMap in_map, out_map;
   {   // index planes sub[j*ny + y, i*nx + x, c] as (x words, i, y, j, frame) -> smem [j][i][384 bytes]
@@ -743,6 +770,61 @@ int launch_decode_tc(const DecArgs& a, cudaStream_t s) {
     for (int r = 0; r < 10; ++r)
       if (h[r * 8]) fprintf(stderr, "[tc prof] %-5s total %lld  wait0 %lld  wait1 %lld  wait2 %lld  wait3 %lld\n", r < 8 ? names[r] : names2[r - 8], h[r * 8], h[r * 8 + 1], h[r * 8 + 2], h[r * 8 + 3], h[r * 8 + 4]);
   }
+  return VCFB_OK;
+}
+
+// B = 8, YCoCg, subband layout, q a power of two >= 8 (|index| <= 128 so the int8 pack cannot saturate):
+// the fast-mode encoder (VCFB_F_FAST).  Everything else -> VCFB_E_UNSUPP -> the bit-exact encoders.
+int launch_encode_tc(const EncArgs& a, cudaStream_t s) {
+  const Geom& g = a.g;
+  if (a.color != VCFB_COLOR_YCOCG || (a.flags & (VCFB_F_NO_SUBBANDS | VCFB_F_PERCEPTUAL | VCFB_F_FP64))) return VCFB_E_UNSUPP;
+  if (g.W % 16 != 0 || g.nx % 16 != 0 || g.left != 0) return VCFB_E_UNSUPP;
+  if ((reinterpret_cast<uintptr_t>(a.rgb) & 15) || (reinterpret_cast<uintptr_t>(a.idx) & 15)) return VCFB_E_UNSUPP;
+  if (!a.q_pow2 || a.q < 8.0 || a.q > 1024.0 || tma::encode_tiled_fn() == nullptr) return VCFB_E_UNSUPP;
+  const unsigned char* ftab = device_table(1);
+  if (!ftab) return VCFB_E_UNSUPP;
+  CUtensorMap in_map, out_map;
+  {   // RGB frames as (W*3/8 uint64, H, n); box = 64 blocks x 8 rows (two per tile)
+    const uint64_t dims[3] = {uint64_t(g.W) * 3 / 8, uint64_t(g.H), uint64_t(a.n_frames)};
+    const uint64_t str[2] = {uint64_t(g.W) * 3, uint64_t(g.H) * g.W * 3};
+    const uint32_t box[3] = {64 * 24 / 8, 8, 1};
+    if (!tma::make_map(&in_map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<uint8_t*>(a.rgb), dims, str, box)) return VCFB_E_UNSUPP;
+  }
+  {   // index planes as (x words, v, y, u, frame) -> smem [u][v][384 bytes]
+    const uint64_t si = uint64_t(g.nx) * 3, sy = uint64_t(g.Wp) * 3, sj = uint64_t(g.ny) * g.Wp * 3,
+                   sf = uint64_t(g.Hp) * g.Wp * 3;
+    const uint64_t dims[5] = {uint64_t(g.nx) * 3 / 4, 8, uint64_t(g.ny), 8, uint64_t(a.n_frames)};
+    const uint64_t str[4] = {si, sy, sj, sf};
+    const uint32_t box[5] = {TB * 3 / 4, 8, 1, 8, 1};
+    if (!tma::make_map(&out_map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 5, a.idx, dims, str, box)) return VCFB_E_UNSUPP;
+  }
+  enc::TcEncArgs ta;
+  ta.tiles_x = (g.nx + TB - 1) / TB;
+  ta.ny = g.ny;
+  ta.nx = g.nx;
+  ta.top = g.top;
+  const long long nt = (long long)a.n_frames * g.ny * ta.tiles_x;
+  if (nt > (0x7fffffffLL - (1 << 20)) / 3) return VCFB_E_UNSUPP;
+  ta.ntiles = int(nt);
+  ta.inv_q = float(a.inv_q);
+  ta.ftab = ftab;
+  int grid = sm_count();
+  if (grid > ta.ntiles) grid = ta.ntiles;
+  const int cfg = dev_cfg("VCFB_TC_ENC_CFG");
+  void (*kern)(const CUtensorMap, const CUtensorMap, const enc::TcEncArgs);
+  int nthreads;
+  switch (cfg) {
+    case 11: kern = enc::enc8_tc_kernel<1, 1>; nthreads = 2 * 128 + 96; break;
+    case 21: kern = enc::enc8_tc_kernel<2, 1>; nthreads = 3 * 128 + 96; break;
+    case 12: kern = enc::enc8_tc_kernel<1, 2>; nthreads = 3 * 128 + 96; break;
+    default: kern = enc::enc8_tc_kernel<2, 2>; nthreads = 4 * 128 + 96; break;
+  }
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, enc::ESMEM);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(enc8_tc)");
+  note_kernel("enc8_tc");
+  kern<<<grid, nthreads, enc::ESMEM, s>>>(in_map, out_map, ta);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "enc8_tc_kernel launch");
   return VCFB_OK;
 }
 
