@@ -376,6 +376,7 @@ struct TcEncArgs {
   int ntiles, tiles_x, ny, nx, top;
   float inv_q;                             // 1 / q, q a power of two
   const unsigned char* ftab;               // HI_BYTES + LO_BYTES, canonical layout
+  long long* prof;
 };
 
 __device__ __forceinline__ unsigned pack_sat_s8(int a, int b, unsigned c) {
@@ -390,7 +391,7 @@ enc8_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
                const TcEncArgs a) {
   constexpr int EPI_THREADS = NGE * 128, CONV_THREADS = NGC * 128, NTHREADS = EPI_THREADS + CONV_THREADS + 96;
   constexpr int W_CONV = EPI_THREADS / 32, W_TMA = (EPI_THREADS + CONV_THREADS) / 32, W_MMA = W_TMA + 1, W_ST = W_TMA + 2;
-  static_assert(NGE == 1 || NGE == 2, "epilogue groups split the coefficient rows 0-3 / 4-7");
+  static_assert(NGE == 1 || NGE == 2, "epilogue groups take the tiles in turn; two output stages");
   static_assert(NGC == 1 || NGC == 2, "converter groups split the pixel rows 0-3 / 4-7");
   extern __shared__ __align__(128) unsigned char smem[];
   EBars* bars = reinterpret_cast<EBars*>(smem + OFF_EBAR);
@@ -409,10 +410,10 @@ enc8_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
     }
     for (int s = 0; s < ND; ++s) {
       tma::mbar_init(&bars->d_full[s], 1);
-      tma::mbar_init(&bars->d_empty[s], 4 * NGE);
+      tma::mbar_init(&bars->d_empty[s], 4);
     }
     for (int s = 0; s < NSOUT; ++s) {
-      tma::mbar_init(&bars->out_full[s], 4 * NGE);
+      tma::mbar_init(&bars->out_full[s], 4);
       tma::mbar_init(&bars->out_free[s], 1);
     }
     tma::fence_mbar_init();
@@ -467,13 +468,17 @@ enc8_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
       constexpr uint32_t IDESC_HI = tc::idesc_f16(TB, NF), IDESC_LO = tc::idesc_f16(TB, 64);
       const uint32_t f_base = tma::smem_u32(smem + OFF_F);
       const uint32_t tb_u = __shfl_sync(0xffffffffu, tbase, 0);
+      TCP_ON(long long eprof[2] = {0, 0}; const long long te0 = clock64();)
       int it = 0;                            // item = (tile, channel)
       for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
 #pragma unroll
         for (int c = 0; c < 3; ++c, ++it) {
           const int sa = it % NA, sd = it % ND;
+          TCP_ON(const long long tw0 = clock64();)
           tc::mbar_wait(&bars->d_empty[sd], ((it / ND) & 1) ^ 1);
+          TCP_ON(const long long tw1 = clock64();)
           tc::mbar_wait(&bars->a_full[sa], (it / NA) & 1);
+          TCP_ON(const long long tw2 = clock64(); eprof[0] += tw1 - tw0; eprof[1] += tw2 - tw1;)
           tc::fence_after();
           if (tc::elect_one()) {
             const uint32_t d_t = tb_u + sd * D_ITEM, a_t = tb_u + A_COL0 + sa * A_ITEM;
@@ -489,6 +494,7 @@ enc8_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
           __syncwarp();
         }
       }
+      TCP_ON(if (a.prof && blockIdx.x == 0 && lane == 0) { a.prof[0] = clock64() - te0; a.prof[1] = eprof[0]; a.prof[2] = eprof[1]; })
     }
   } else if (warp >= W_CONV) {
     // ===== converter: thread = (block, 8 / NGC pixel rows) =====
@@ -499,10 +505,13 @@ enc8_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
     const __half2 sub_y = __floats2half2_rn(1536.0f, 1536.0f);      // 1024 + 512      : R + 2G + B - 512 = 4Y
     const __half2 sub_co = __floats2half2_rn(1280.0f, 1280.0f);     // 1024 + 256      : R - B = 2Co
     const __half2 sub_cg = __floats2half2_rn(1536.0f, 1536.0f);     // 1024 + 512      : -R + 2G - B = 4Cg
+    TCP_ON(long long cw[3] = {0, 0, 0}; const long long tcv0 = clock64();)
     int k = 0;
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++k) {
       const int s = k % NSIN;
+      TCP_ON(const long long tv0 = clock64();)
       tc::mbar_wait(&bars->in_full[s], (k / NSIN) & 1);
+      TCP_ON(const long long tv1 = clock64(); cw[0] += tv1 - tv0;)
       const unsigned char* tp = smem + OFF_IN + s * RGB_TILE + (b >> 6) * (RGB_TILE / 2) + (b & 63) * 24 + grp * NRW * (64 * 24);
       uint32_t w[3][4 * NRW];
 #pragma unroll
@@ -528,11 +537,14 @@ enc8_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
         }
       }
       __syncwarp();
+      TCP_ON(cw[1] += clock64() - tv1;)
       if (lane == 0) tc::mbar_arrive(&bars->in_empty[s]);
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const int it = 3 * k + c, sa = it % NA;
+        TCP_ON(const long long tv2 = clock64();)
         tc::mbar_wait(&bars->a_empty[sa], ((it / NA) & 1) ^ 1);
+        TCP_ON(cw[2] += clock64() - tv2;)
 #pragma unroll
         for (int j = 0; j < NRW / 2; ++j) tc::st8(tbase + lane_off + A_COL0 + sa * A_ITEM + grp * 4 * NRW + 8 * j, &w[c][8 * j]);
         tc::wait_st();
@@ -541,87 +553,106 @@ enc8_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
         if (lane == 0) tc::mbar_arrive(&bars->a_full[sa]);
       }
     }
+    TCP_ON(if (a.prof && blockIdx.x == 0 && threadIdx.x == W_CONV * 32) { a.prof[8] = clock64() - tcv0; a.prof[9] = cw[0]; a.prof[10] = cw[1]; a.prof[11] = cw[2]; })
   } else {
-    // ===== epilogue: thread = (block = TMEM lane, 8 / NGE coefficient rows u) =====
+    // ===== epilogue: thread = block = TMEM lane; the NGE warp groups take the tiles in turn, so the latency of a
+    // tile's chain (barrier -> tensor-memory load -> quantise -> shuffle -> store) is hidden behind the other group =====
     const int b = threadIdx.x & 127, grp = warp >> 2;
     const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
-    constexpr int NU = 8 / NGE;
     constexpr float SQ2 = 0x1.6a09e6p+0f, SQ2H = 0x1.6a09e6p-1f;     // pocketfft's float32 constants (dct8_fwd: t67, t66)
+    // the index tile is written as aligned words: the 4 blocks of a lane quad own 12 consecutive bytes of a row
+    const int qj = lane & 3;                             // lane j < 3 of the quad writes word j
+    const uint32_t wsel = qj == 0 ? 0x4210u : (qj == 1 ? 0x5421u : 0x6542u);
+    TCP_ON(long long pw[3] = {0, 0, 0}; const long long tp0 = clock64();)
     int k = 0;
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++k) {
-      const int st = k & 1;
-      unsigned char* ob = smem + OFF_OUTI + st * IDXT + 3 * b;
+      if (k % NGE != grp) continue;
+      const int st = k & 1, ku = k / NGE;                // ku: how many tiles this group has done
+      uint32_t hold[3][2][4][2];                         // [channel][half][row][4 index bytes each]
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         const int it = 3 * k + c, sd = it % ND;
         // coefficient = D / (4096 * colour scale): the converter fed 4Y, 2Co, 4Cg
         const float sc = a.inv_q * (c == 1 ? 0x1p-13f : 0x1p-14f);
+        TCP_ON(const long long tq0 = clock64();)
         tc::mbar_wait(&bars->d_full[sd], (it / ND) & 1);
+        TCP_ON(pw[0] += clock64() - tq0;)
         tc::fence_after();
         const uint32_t dcol = tbase + lane_off + sd * D_ITEM;
-        // ---- the rational coefficients of this group's rows: (0,0) (0,4) for u = 0, (4,0) (4,4) for u = 4 ----
-        float r0[NGE == 1 ? 2 : 1], r4[NGE == 1 ? 2 : 1];
+        uint32_t sv[16];
+        uint32_t dv[32];
+        tc::ld16(dcol + 64, sv);                          // the sums of the rational positions travel with the first half
+        tc::ld32(dcol, dv);
+        tc::wait_ld();
 #pragma unroll
-        for (int h = 0; h < (NGE == 1 ? 2 : 1); ++h) {
-          const int uu = NGE == 1 ? 4 * h : 4 * grp;       // 0 or 4
-          uint32_t sv[8];
-          tc::ld8(dcol + 64 + 2 * uu, sv);                  // S0 at columns 64..71, S4 at 72..79
-          tc::wait_ld();
-          float p[8];
-          const float cm = uu == 0 ? SQ2 : SQ2H;            // pass 1 (over the rows): output 0 * sqrt(2), output 4 * sqrt(1/2)
+        for (int h = 0; h < 2; ++h) {
+          const int uu = 4 * h;                           // first row of the half: 0 or 4, the rows with rational positions
+          // ---- the rational coefficients (uu, 0) and (uu, 4), exactly as dct_codelets.cuh::dct8_fwd rounds them ----
+          float r0, r4;
+          {
+            float p[8];
+            const float cm = uu == 0 ? SQ2 : SQ2H;          // pass 1 (over the rows): output 0 * sqrt(2), output 4 * sqrt(1/2)
 #pragma unroll
-          for (int x = 0; x < 8; ++x) p[x] = __fmul_rn(__uint_as_float(sv[x]), cm);
-          // pass 2 (over x): dct8_fwd's own additions for its outputs 0 and 4
-          const float t9 = __fadd_rn(p[1], p[2]), t13 = __fadd_rn(p[5], p[6]), t11 = __fadd_rn(p[3], p[4]), t14 = __fadd_rn(p[0], p[7]);
-          const float t16 = __fadd_rn(t9, t13), t27 = __fadd_rn(t11, t14);
-          const float t29 = __fadd_rn(t16, t27), t30 = __fsub_rn(t27, t16);
-          // lazy powers of two: outputs 0 carry 2^-2, outputs 4 carry 2^-1, per pass
-          const float e_u = uu == 0 ? 0.25f : 0.5f;
-          r0[h] = __fmul_rn(t29, SQ2) * (e_u * 0.25f);
-          r4[h] = __fmul_rn(t30, SQ2H) * (e_u * 0.5f);
-        }
-        if (c == 0) tc::mbar_wait(&bars->out_free[st], ((k >> 1) & 1) ^ 1);   // the store that last read this stage is done
+            for (int x = 0; x < 8; ++x) p[x] = __fmul_rn(__uint_as_float(sv[8 * h + x]), cm);
+            // pass 2 (over x): dct8_fwd's own additions for its outputs 0 and 4
+            const float t9 = __fadd_rn(p[1], p[2]), t13 = __fadd_rn(p[5], p[6]), t11 = __fadd_rn(p[3], p[4]), t14 = __fadd_rn(p[0], p[7]);
+            const float t16 = __fadd_rn(t9, t13), t27 = __fadd_rn(t11, t14);
+            const float t29 = __fadd_rn(t16, t27), t30 = __fsub_rn(t27, t16);
+            // lazy powers of two: output 0 carries 2^-2, output 4 carries 2^-1, per pass; colour scale; 1 / q
+            const float e_u = (uu == 0 ? 0.25f : 0.5f) * a.inv_q * (c == 1 ? 0.5f : 0.25f);
+            r0 = __fmul_rn(t29, SQ2) * (e_u * 0.25f);
+            r4 = __fmul_rn(t30, SQ2H) * (e_u * 0.5f);
+          }
 #pragma unroll
-        for (int ur = 0; ur < NU; ++ur) {
-          const int u = grp * NU + ur;
-          uint32_t dv[8];
-          tc::ld8(dcol + 8 * u, dv);
-          tc::wait_ld();
-          if (ur == NU - 1) {                // D is in registers: hand the item back to the MMA warp
-            tc::fence_before();
+          for (int ur = 0; ur < 4; ++ur) {
+            float v[8];
+#pragma unroll
+            for (int x = 0; x < 8; ++x) v[x] = __uint_as_float(dv[8 * ur + x]) * sc;
+            if (ur == 0) {
+              v[0] = r0;
+              v[4] = r4;
+            }
+            // truncate toward zero, saturating pack to int8 (|index| <= 128 here), + 128 as a flip of the top bit (the
+            // reference's astype(uint8) wrap and this coincide for indices in [-128, 127])
+            hold[c][h][ur][0] = pack_sat_s8(__float2int_rz(v[1]), __float2int_rz(v[0]),
+                                            pack_sat_s8(__float2int_rz(v[3]), __float2int_rz(v[2]), 0u)) ^ 0x80808080u;
+            hold[c][h][ur][1] = pack_sat_s8(__float2int_rz(v[5]), __float2int_rz(v[4]),
+                                            pack_sat_s8(__float2int_rz(v[7]), __float2int_rz(v[6]), 0u)) ^ 0x80808080u;
+          }
+          if (h == 0) {
+            tc::ld32(dcol + 32, dv);
+            tc::wait_ld();
+            tc::fence_before();              // D is in registers: hand the item back to the MMA warp
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&bars->d_empty[sd]);
           }
-          float v[8];
-#pragma unroll
-          for (int x = 0; x < 8; ++x) v[x] = __uint_as_float(dv[x]) * sc;
-          if (u == 0 || u == 4) {            // compile-time after unrolling when NGE == 1; uniform per group otherwise
-            const int h = NGE == 1 ? (u >> 2) : 0;
-            const float cs = a.inv_q * (c == 1 ? 0.5f : 0.25f);
-            v[0] = r0[h] * cs;
-            v[4] = r4[h] * cs;
-          }
-          // truncate toward zero, saturating pack to int8 (|index| <= 128 / q * 8 <= 128 here), + 128 as a flip of
-          // the top bit (the reference's astype(uint8) wrap and this coincide for indices in [-128, 127])
-          const unsigned w0 = pack_sat_s8(__float2int_rz(v[1]), __float2int_rz(v[0]),
-                                          pack_sat_s8(__float2int_rz(v[3]), __float2int_rz(v[2]), 0u)) ^ 0x80808080u;
-          const unsigned w1 = pack_sat_s8(__float2int_rz(v[5]), __float2int_rz(v[4]),
-                                          pack_sat_s8(__float2int_rz(v[7]), __float2int_rz(v[6]), 0u)) ^ 0x80808080u;
-          unsigned char* o = ob + (8 * u) * (TB * 3) + c;
-          o[0 * TB * 3] = (unsigned char)(w0);
-          o[1 * TB * 3] = (unsigned char)(w0 >> 8);
-          o[2 * TB * 3] = (unsigned char)(w0 >> 16);
-          o[3 * TB * 3] = (unsigned char)(w0 >> 24);
-          o[4 * TB * 3] = (unsigned char)(w1);
-          o[5 * TB * 3] = (unsigned char)(w1 >> 8);
-          o[6 * TB * 3] = (unsigned char)(w1 >> 16);
-          o[7 * TB * 3] = (unsigned char)(w1 >> 24);
         }
       }
+      // ---- the three channels of the block are in registers: write rows [8u + v][3 block + channel] as words ----
+      TCP_ON(const long long tq1 = clock64();)
+      tc::mbar_wait(&bars->out_free[st], ((k >> 1) & 1) ^ 1);       // the store that last read this stage is done
+      TCP_ON(const long long tq2 = clock64(); pw[1] += tq2 - tq1;)
+      uint32_t* ow = reinterpret_cast<uint32_t*>(smem + OFF_OUTI + st * IDXT) + 3 * (b >> 2) + qj;
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int ur = 0; ur < 4; ++ur)
+#pragma unroll
+          for (int x = 0; x < 8; ++x) {
+            const int u = 4 * h + ur;
+            // this block's (Y, Co, Cg) bytes of coefficient (u, x)
+            const uint32_t yc = __byte_perm(hold[0][h][ur][x >> 2], hold[1][h][ur][x >> 2], 0x0040 + 0x0011 * (x & 3));
+            const uint32_t mine = __byte_perm(yc, hold[2][h][ur][x >> 2], 0x0010 + 0x0400 + 0x0100 * (x & 3));
+            const uint32_t next = __shfl_down_sync(0xffffffffu, mine, 1);
+            if (qj < 3) ow[(8 * u + x) * (TB * 3 / 4)] = __byte_perm(mine, next, wsel);
+          }
       tma::fence_proxy_async();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&bars->out_full[st]);
+      TCP_ON(pw[2] += clock64() - tq2;)
+      (void)ku;
     }
+    TCP_ON(if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) { a.prof[4] = clock64() - tp0; a.prof[5] = pw[0]; a.prof[6] = pw[1]; a.prof[7] = pw[2]; })
   }
 
   tc::fence_before();
@@ -808,16 +839,22 @@ int launch_encode_tc(const EncArgs& a, cudaStream_t s) {
   ta.ntiles = int(nt);
   ta.inv_q = float(a.inv_q);
   ta.ftab = ftab;
+  ta.prof = nullptr;
+#ifdef VCFB_TC_PROFILE
+  static long long* eprof_buf = nullptr;
+  if (!eprof_buf) cudaMalloc(reinterpret_cast<void**>(&eprof_buf), 128);
+  ta.prof = eprof_buf;
+#endif
   int grid = sm_count();
   if (grid > ta.ntiles) grid = ta.ntiles;
   const int cfg = dev_cfg("VCFB_TC_ENC_CFG");
   void (*kern)(const CUtensorMap, const CUtensorMap, const enc::TcEncArgs);
   int nthreads;
   switch (cfg) {
-    case 11: kern = enc::enc8_tc_kernel<1, 1>; nthreads = 2 * 128 + 96; break;
     case 21: kern = enc::enc8_tc_kernel<2, 1>; nthreads = 3 * 128 + 96; break;
     case 12: kern = enc::enc8_tc_kernel<1, 2>; nthreads = 3 * 128 + 96; break;
-    default: kern = enc::enc8_tc_kernel<2, 2>; nthreads = 4 * 128 + 96; break;
+    case 22: kern = enc::enc8_tc_kernel<2, 2>; nthreads = 4 * 128 + 96; break;
+    default: kern = enc::enc8_tc_kernel<1, 1>; nthreads = 2 * 128 + 96; break;      // measured fastest (0.69 ms per 64 4K frames)
   }
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, enc::ESMEM);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(enc8_tc)");
@@ -825,6 +862,15 @@ int launch_encode_tc(const EncArgs& a, cudaStream_t s) {
   kern<<<grid, nthreads, enc::ESMEM, s>>>(in_map, out_map, ta);
   e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "enc8_tc_kernel launch");
+#ifdef VCFB_TC_PROFILE
+  {
+    long long h[12];
+    cudaStreamSynchronize(s);
+    cudaMemcpy(h, ta.prof, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[tc enc prof] mma total %lld  wait d_empty %lld  a_full %lld | epi total %lld  wait d_full %lld  out_free %lld  store phase %lld | conv total %lld  wait in_full %lld  convert %lld  wait a_empty %lld  (%d tiles per CTA)\n",
+            h[0], h[1], h[2], h[4], h[5], h[6], h[7], h[8], h[9], h[10], h[11], (ta.ntiles + grid - 1) / grid);
+  }
+#endif
   return VCFB_OK;
 }
 
