@@ -1,12 +1,13 @@
-'''Intra-only sequence coding: every frame goes through the 2D codec, the whole sequence as one GPU batch.'''
+'''Intra-only sequence coding: every frame goes through the 2D codec, in pipelined GPU chunks.'''
 
 # Batched counterpart of the reference's src/III.py.  Same flags (-T transform, -N
 # number_of_frames, src/III.py:23-32), same file names (/tmp/original_%04d.png,
 # /tmp/encoded_%04d<ext> + _shape.bin, /tmp/decoded_%04d.png, :85-86, :133-134) and the same
 # per-frame results as calling the transform's encode_fn / decode_fn once per frame (what
-# :96-104 intends and :132-144 does) -- but the frames are read first, transformed as ONE
-# batch on the GPU (sharded by contiguous frame ranges over the ranks when launched with
-# torchrun, vcf_b200.frames), and entropy-coded / written by a pool of host threads.
+# :96-104 intends and :132-144 does) -- but the frames travel in chunks through a fixed-depth
+# ring of pinned buffers (vcf_b200/pipeline.py): while one chunk is on the GPU the previous one
+# is entropy-coded / written and the next one is read by a pool of host threads.  Under
+# torchrun the sequence is sharded by contiguous frame ranges, one rank per GPU (vcf_b200.frames).
 # The entropy coder and the file formats are the chain's own (compress / decompress /
 # encode_write_fn / decode_write_fn of the -c codec), so either side can be the reference.
 
@@ -15,7 +16,6 @@ import logging
 import os
 import struct
 import sys
-from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -31,6 +31,7 @@ with open("/tmp/description.txt", 'w') as f:
 import parser  # noqa: E402
 
 from vcf_b200.frames import frame_range  # noqa: E402
+from vcf_b200.pipeline import ChunkPipeline  # noqa: E402
 
 DEFAULT_TRANSFORM = "2D-DCT-B200"
 N_FRAMES = 20                      # src/video_coding.py:29
@@ -42,6 +43,8 @@ for _p in (parser.parser_encode, parser.parser_decode):
     _p.add_argument("-T", "--transform", type=str, help=f"module of the 2D codec (default {DEFAULT_TRANSFORM})", default=DEFAULT_TRANSFORM)
     _p.add_argument("-N", "--number_of_frames", type=parser.int_or_str, help=f"how many frames of the sequence to code (default {N_FRAMES})", default=N_FRAMES)
     _p.add_argument("--io_threads", type=int, default=8, help="host threads for entropy coding and file IO")
+    _p.add_argument("--chunk_frames", type=int, default=8, help="frames per GPU chunk of the pipeline")
+    _p.add_argument("--pipeline_depth", type=int, default=3, help="chunks in flight: one being read, one on the GPU, one being written")
 
 args = parser.parser.parse_known_args()[0]
 transform = importlib.import_module(args.transform)
@@ -121,29 +124,26 @@ class CoDec:
         lo, hi = frame_range(n, rank, world)
         if hi == lo:
             return 0
-        with ThreadPoolExecutor(self.args.io_threads) as pool:
-            frames = list(pool.map(lambda i: tc.encode_read_fn(f"{ORIGINAL_PREFIX}_%04d.png" % i), range(lo, hi)))
-            for fr in frames:
-                tc._check_image(fr)
-            if len({fr.shape for fr in frames}) != 1:
-                raise ValueError("all frames of a sequence must have the same shape")
-            batch = np.ascontiguousarray(np.stack(frames))
-            if getattr(tc, "accepts_device_arrays", False):
-                # the entropy stage runs on the GPU too (-c z_lib-B200): the indices never leave HBM,
-                # only the code-streams come back
-                import torch
-                idx_dev = tc._codec().encode(torch.from_numpy(batch).cuda())       # one GPU batch
-                streams = [tc.compress(idx_dev[j]) for j in range(hi - lo)]
-            else:
-                idx = tc._codec().encode(batch)                                     # one GPU batch
-                streams = None
+        codec = tc._codec()
+        gpu_entropy = bool(getattr(tc, "accepts_device_arrays", False))
+        shapes = {}
 
-            def finish(j):
-                out_fn = f"{ENCODE_OUTPUT_PREFIX}_%04d" % (lo + j)
-                with open(f"{out_fn}_shape.bin", "wb") as file:
-                    file.write(struct.pack("iii", *frames[j].shape))
-                return tc.encode_write_fn(streams[j] if streams is not None else tc.compress(idx[j]), out_fn)
-            sizes = list(pool.map(finish, range(hi - lo)))
+        def read(i):
+            fr = tc.encode_read_fn(f"{ORIGINAL_PREFIX}_%04d.png" % i)
+            tc._check_image(fr)
+            shapes[i] = fr.shape
+            return fr
+
+        def finish(i, k, on_device):
+            out_fn = f"{ENCODE_OUTPUT_PREFIX}_%04d" % i
+            with open(f"{out_fn}_shape.bin", "wb") as file:           # src/2D-DCT.py:285-286
+                file.write(struct.pack("iii", *shapes[i]))
+            # the entropy stage of the chain (host zlib / TIFF), or the GPU one fed from HBM (-c z_lib-B200 / TIFF-B200)
+            return tc.encode_write_fn(tc.compress(k if on_device else np.array(k)), out_fn)
+
+        pipe = ChunkPipeline(device=self.device, depth=self.args.pipeline_depth, chunk=self.args.chunk_frames,
+                             io_threads=self.args.io_threads, keep_on_device=gpu_entropy)
+        sizes = pipe.run(hi - lo, read, lambda x, m: codec.encode(x), finish, first=lo)
         logging.info(f"rank {rank}: frames [{lo},{hi}) -> {sum(sizes)} bytes")
         return sum(sizes)
 
@@ -154,21 +154,35 @@ class CoDec:
         lo, hi = frame_range(n, rank, world)
         if hi == lo:
             return 0
-        with ThreadPoolExecutor(self.args.io_threads) as pool:
-            def load(i):
-                in_fn = f"{ENCODE_OUTPUT_PREFIX}_%04d" % i
-                with open(f"{in_fn}_shape.bin", "rb") as file:
-                    shape = struct.unpack("iii", file.read(12))
-                return shape, np.ascontiguousarray(tc.decompress(tc.decode_read_fn(in_fn)))
-            items = list(pool.map(load, range(lo, hi)))
-            shapes = {s for s, _ in items}
-            if len(shapes) != 1:
+        if getattr(self.args, "filter", "no_filter") != "no_filter":
+            # a real post-filter needs the un-clipped float image of every frame (src/2D-DCT.py:454-466):
+            # the transform stage's own decode_fn does exactly that
+            return sum(tc.decode_fn(f"{ENCODE_OUTPUT_PREFIX}_%04d" % i, f"{DECODE_OUTPUT_PREFIX}_%04d.png" % i)
+                       for i in range(lo, hi))
+        codec = tc._codec(decode=True)
+        shapes = {}
+
+        def read(i):
+            in_fn = f"{ENCODE_OUTPUT_PREFIX}_%04d" % i
+            with open(f"{in_fn}_shape.bin", "rb") as file:
+                shapes[i] = struct.unpack("iii", file.read(12))
+            k = np.ascontiguousarray(tc.decompress(tc.decode_read_fn(in_fn)))
+            if k.dtype != np.uint8:
+                raise ValueError(f"code-stream holds {k.dtype}, expected uint8 indices")
+            return k
+
+        def gpu(k, m):
+            shape = shapes[lo]
+            if len({shapes[i] for i in shapes}) != 1:
                 raise ValueError("all frames of a sequence must have the same shape")
-            shape = shapes.pop()
-            y = tc._codec(decode=True).decode(np.stack([k for _, k in items]), shape[:2])   # one GPU batch
-            sizes = list(pool.map(lambda j: tc.decode_write_fn(y[j], f"{DECODE_OUTPUT_PREFIX}_%04d.png" % (lo + j)),
-                                  range(hi - lo)))
-        return sum(sizes)
+            return codec.decode(k, shape[:2])
+
+        def finish(i, y, on_device):
+            return tc.decode_write_fn(np.array(y), f"{DECODE_OUTPUT_PREFIX}_%04d.png" % i)
+
+        pipe = ChunkPipeline(device=self.device, depth=self.args.pipeline_depth, chunk=self.args.chunk_frames,
+                             io_threads=self.args.io_threads)
+        return sum(pipe.run(hi - lo, read, gpu, finish, first=lo))
 
 
 if __name__ == "__main__":
