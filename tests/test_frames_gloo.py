@@ -46,6 +46,16 @@ def _worker(rank, world, port, q):
         v = np.arange(_lib.STAT_LEN, dtype=np.int64) * (rank + 1)
         tot = allreduce_stats(v.copy())
         assert np.array_equal(tot, np.arange(_lib.STAT_LEN, dtype=np.int64) * sum(range(1, world + 1)))
+        # 1b) the asynchronous form used by batch loops: several reductions in flight, waited for later
+        import torch
+        pend = []
+        for b in range(3):
+            t = torch.arange(_lib.STAT_LEN, dtype=torch.int64) * (rank + 1 + b)
+            pend.append((b, *allreduce_stats(t, async_op=True)))
+        for b, t, work in pend:
+            assert work is not None
+            work.wait()
+            assert torch.equal(t, torch.arange(_lib.STAT_LEN, dtype=torch.int64) * sum(r + 1 + b for r in range(world)))
         # 2) sharded round-trip statistics with an oracle-backed stand-in for the GPU
         #    codec (test double only: the product class has no CPU path)
         n, H, W, B, qq = 5, 32, 48, 8, 16

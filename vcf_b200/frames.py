@@ -25,17 +25,25 @@ def frame_range(n_frames: int, rank: int, world: int):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
-def allreduce_stats(vec, group=None):
+def allreduce_stats(vec, group=None, async_op: bool = False):
     """Sum the statistics vector over all ranks (NCCL for CUDA tensors, gloo for CPU
-    tensors / numpy).  Returns the same kind of object it was given."""
+    tensors / numpy).  Returns the same kind of object it was given.
+
+    async_op=True (CUDA tensors): returns ``(tensor, work)``; the reduction runs on NCCL's own
+    stream beside the kernels launched afterwards, and ``work.wait()`` (``None`` on a single
+    rank) makes the current stream wait for it -- a batch loop waits for batch i while batch
+    i+1 is already being transformed, which takes the collective off the critical path."""
     import torch
     import torch.distributed as dist
     is_np = isinstance(vec, np.ndarray)
     t = torch.from_numpy(np.ascontiguousarray(vec, dtype=np.int64)) if is_np else vec
     if t.numel() != STAT_LEN or t.dtype != torch.int64:
         raise ValueError("statistics vector must be int64[%d]" % STAT_LEN)
+    work = None
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        work = dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+    if async_op:
+        return (t.numpy() if is_np else t), work
     return t.numpy() if is_np else t
 
 
