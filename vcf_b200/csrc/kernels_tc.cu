@@ -455,10 +455,10 @@ enc8_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
         const int f = tile / per_frame, rem = tile - f * per_frame, by = rem / a.tiles_x, tx = rem - by * a.tiles_x;
         tma::store_5d(&out_map, smem + OFF_OUTI + st * IDXT, tx * (TB * 3 / 4), 0, by, 0, f);
         tma::commit_group();
-        if (k >= 1) {
-          tma::wait_group_read<1>();
-          tc::mbar_arrive(&bars->out_free[st ^ 1]);
-        }
+        // hand the stage back as soon as THIS store has read it (a few hundred cycles): the epilogue groups own one
+        // output stage each, and waiting for the next tile's store would chain their store phases to each other
+        tma::wait_group_read<0>();
+        tc::mbar_arrive(&bars->out_free[st]);
       }
       tma::wait_group<0>();
     }
@@ -853,8 +853,8 @@ int launch_encode_tc(const EncArgs& a, cudaStream_t s) {
   switch (cfg) {
     case 21: kern = enc::enc8_tc_kernel<2, 1>; nthreads = 3 * 128 + 96; break;
     case 12: kern = enc::enc8_tc_kernel<1, 2>; nthreads = 3 * 128 + 96; break;
-    case 22: kern = enc::enc8_tc_kernel<2, 2>; nthreads = 4 * 128 + 96; break;
-    default: kern = enc::enc8_tc_kernel<1, 1>; nthreads = 2 * 128 + 96; break;      // measured fastest (0.69 ms per 64 4K frames)
+    case 11: kern = enc::enc8_tc_kernel<1, 1>; nthreads = 2 * 128 + 96; break;
+    default: kern = enc::enc8_tc_kernel<2, 2>; nthreads = 4 * 128 + 96; break;      // measured fastest (0.66 ms per 64 4K noise frames)
   }
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, enc::ESMEM);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(enc8_tc)");
