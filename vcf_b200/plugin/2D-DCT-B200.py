@@ -51,6 +51,7 @@ for _p in (parser.parser_encode, parser.parser_decode):
 parser.parser_encode.add_argument("-L", "--Lambda", type=parser.int_or_str, help="when given (float): pick the block size in {4, 8, 16, 32} minimising bytes + Lambda * RMSE")
 parser.parser_decode.add_argument("--b200_fast_decode", action='store_true', help="float32 GPU decoder (pixels within +-1 of the reference, PSNR within 0.01 dB) instead of the bit-exact float64 one", default=False)
 
+parser.parser_encode.add_argument("--b200_fast_encode", action='store_true', help="tensor-core GPU encoder (B = 8, q a power of two >= 8): fewer than 1e-6 of the indices differ from the reference, only at rounding boundaries", default=False)
 parser.parser_decode.add_argument("--b200_synth_f32", action='store_true', help="float64 GPU decoder in the upstream variant that stores the synthesised image as float32 (see include/vcfb200.h VCFB_F_SYNTH_F32)", default=False)
 
 args = parser.parser.parse_known_args()[0]
@@ -88,12 +89,13 @@ class CoDec(CT.CoDec):
             raise ValueError(f"block size {B} is not supported by the GPU path (supported: {SUPPORTED_B})")
         fp64 = decode and not getattr(self.args, "b200_fast_decode", False)
         synth32 = fp64 and bool(getattr(self.args, "b200_synth_f32", False))
-        key = (B, fp64, synth32)
+        fast = (not decode) and bool(getattr(self.args, "b200_fast_encode", False))
+        key = (B, fp64, synth32, fast)
         if key not in self._codecs:
             # ``-t`` only selects the base class in the reference; the arithmetic is
             # always YCoCg (src/2D-DCT.py:22-23, :298, :449).
             self._codecs[key] = Codec(block_size=B, q=self.QSS, color="YCoCg", perceptual=self.perceptual,
-                                      disable_subbands=self.disable_subbands, fp64=fp64, synth_f32=synth32,
+                                      disable_subbands=self.disable_subbands, fp64=fp64, synth_f32=synth32, fast=fast,
                                       device=getattr(self, "device", None))
         return self._codecs[key]
 
