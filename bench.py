@@ -285,9 +285,9 @@ def run_reference(a):
     v = sum(per_step) / len(per_step)
     base["value"] = v
     px = base["cores"] * H * W
-    cfg = main_config(a.frames, max(1, a.gpus))
-    cfg["sample_note"] = "each step of this arm is a bounded sample of the workload: one frame per host core"
+    cfg = main_config(a.frames, max(1, a.gpus))      # identical to the GPU arm's: same workload, same content generator
     line = dict(impl="reference", metric=METRIC, value=v, unit="Mpixel/s",
+                sample_note="each step of this arm is a bounded sample of the workload: one frame per host core",
                 n_gpus=a.gpus, steps=a.steps, warmup=a.warmup, ms_per_step=px / 1e6 / v * 1e3,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32 encode / f64 decode",
                 data="synthetic", config=cfg, cpu_baseline=base,
