@@ -82,3 +82,31 @@ def test_pruned_inverse_codelets_are_bit_exact():
                 want = sf.idct(x, norm="ortho")
                 assert want.dtype == dtype
                 assert np.array_equal(got, want), (nin, dtype, x, got, want)
+
+
+def test_dag_programs_in_sync_with_generator():
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "vcf_b200", "codegen", "gen_dag_programs.py"), "--check"], cwd=ROOT)
+    assert r.returncode == 0, "run `python vcf_b200/codegen/gen_dag_programs.py` and commit vcf_b200/csrc/dag_programs.inc"
+
+
+def test_dag_programs_are_bit_exact():
+    """The interpreted programs of csrc/kernels_anyb.cu (block sizes 2, 64, 128 of the reference's -L search,
+    src/2D-DCT.py:538) through the numpy twin of the device interpreter, against the real scipy: bitwise,
+    float32 and float64, both directions."""
+    import numpy as np
+    import scipy.fftpack as sf
+    sys.path.insert(0, ROOT)
+    from vcf_b200.codegen import gen_dag_programs as G
+    rng = np.random.default_rng(5)
+    for n in G.SIZES:
+        for inverse in (False, True):
+            ops, consts, outs, nslots = G.program(n, inverse)
+            assert nslots <= 138
+            for dtype in (np.float32, np.float64):
+                x = rng.integers(-2048, 2048, size=(3000, n)).astype(dtype)
+                x[::7] *= dtype(0.25)
+                x[1::11, n // 2:] = 0
+                got = G.interpret(ops, consts, outs, nslots, x, dtype)
+                want = (sf.idct if inverse else sf.dct)(x, norm="ortho", axis=-1)
+                assert want.dtype == dtype
+                assert np.array_equal(got, want), (n, inverse, dtype)

@@ -95,6 +95,52 @@ def test_decode_fp64_bit_exact_and_fp32_within_1lsb(B, q, torch_cuda):
             assert abs(O.psnr(img, got32) - O.psnr(img, ref)) < 0.1, (B, q, H, W)
 
 
+@pytest.mark.parametrize("B", [2, 64, 128])
+def test_block_sizes_of_the_L_search_without_a_codelet(B, torch_cuda):
+    """B = 2, 64, 128 -- the rest of the set `optimize_block_size` tries (src/2D-DCT.py:538) -- run as
+    interpreted pocketfft programs (csrc/kernels_anyb.cu): bit-exact like every other size, every flag."""
+    from vcf_b200 import _lib
+    shapes = [(128, 256), (67, 91), (5, 3), (130, 200)]
+    for si, (H, W) in enumerate(shapes):
+        for kind in ("noise", "natural"):
+            img = O.synthetic_frame(H, W, 900 + si, kind)
+            for q in (1, 12, 32):
+                for fp64, dt in ((False, np.float32), (True, np.float64)):
+                    ref = O.encode_array(img, B, q, dtype=dt)
+                    got = _codec(block_size=B, q=q, fp64=fp64).encode(img)
+                    assert _lib.lib().vcfb_last_kernel() == b"encode_anyb"
+                    assert got.shape == ref.shape and np.array_equal(got, ref), (B, q, H, W, kind, fp64)
+                idx = O.encode_array(img, B, q)
+                ref = O.decode_array(idx, img.shape, B, q)
+                got = _codec(block_size=B, q=q, fp64=True).decode(idx, img.shape)
+                assert _lib.lib().vcfb_last_kernel() == b"decode_anyb"
+                assert np.array_equal(got, ref), (B, q, H, W, kind)
+    img = O.synthetic_frame(128, 256, 950, "natural")
+    for kw in (dict(disable_subbands=True), dict(perceptual=True), dict(color="YCrCb")):
+        ref = O.encode_array(img, B, 8, **kw)
+        got = _codec(block_size=B, q=8, **kw).encode(img)
+        assert np.array_equal(got, ref), (B, kw)
+        refd = O.decode_array(ref, img.shape, B, 8, **kw)
+        gotd = _codec(block_size=B, q=8, fp64=True, **kw).decode(ref, img.shape)
+        assert np.array_equal(gotd, refd), (B, kw)
+    # a batch, statistics on both sides, float output
+    t = torch_cuda
+    batch = np.stack([O.synthetic_frame(128, 128, 960 + i, "natural") for i in range(3)])
+    enc, dec = _codec(block_size=B, q=16), _codec(block_size=B, q=16, fp64=True)
+    idx, se = enc.encode(t.from_numpy(batch).cuda(), stats=True)
+    ref = np.stack([O.encode_array(f, B, 16) for f in batch])
+    assert np.array_equal(idx.cpu().numpy(), ref)
+    out, yf, sd = dec.decode(idx, (128, 128), original=t.from_numpy(batch).cuda(), stats=True, return_float=True)
+    refd = np.stack([O.decode_array(k, (128, 128, 3), B, 16) for k in ref])
+    assert np.array_equal(out.cpu().numpy(), refd)
+    from vcf_b200.codec import stats_dict
+    st = stats_dict((se + sd).cpu().numpy())
+    d = batch.astype(np.int64) - refd.astype(np.int64)
+    assert int(st["sse"].sum()) == int((d * d).sum()) and st["nsamples"] == batch.size
+    assert st["nonzero"] == int((ref != 128).sum()) and st["nindices"] == ref.size
+    assert np.array_equal(np.clip(yf.cpu().numpy(), 0, 255).astype(np.uint8), refd)
+
+
 def test_random_indices_decode_fp64(torch_cuda):
     """Arbitrary index arrays (not produced by an encoder), incl. the int16 wrap
     of q*k and saturating clips."""

@@ -86,13 +86,13 @@ def test_iii_style_per_frame_loop_and_block_size_optimiser():
         idx = np.load("/tmp/encoded_%04d.npz" % i)["a"]
         assert np.array_equal(idx, O.encode_array(f, 8, 16))
         assert np.array_equal(_read_png("/tmp/decoded_%04d.png" % i), O.decode_array(idx, f.shape, 8, 16))
-    # -L: J = rate + Lambda*RMSE over the supported block sizes (src/2D-DCT.py:533-579)
+    # -L: J = rate + Lambda*RMSE over 2**i, i = 1..7 (src/2D-DCT.py:533-579; 128 does not divide the frame)
     img = frames[0]
     _write_png("/tmp/original.png", img)
     r = _run(STUB, PLUGIN, "encode", "-L", "50.0", "-q", "16", "-g")
     assert r.returncode == 0, r.stderr[-2000:]
     best, bestJ = None, 1e18
-    for B in (4, 8, 16, 32):
+    for B in (2, 4, 8, 16, 32, 64):
         k = O.encode_array(img, B, 16)
         b = io.BytesIO()
         np.savez_compressed(file=b, a=k)

@@ -87,8 +87,8 @@ class Codec:
                  device: Optional[int] = None, hist: bool = True, synth_f32: bool = False, fast: bool = False):
         if color not in _COLORS:
             raise ValueError(f"color must be one of {list(_COLORS)}")
-        if block_size not in (4, 8, 16, 32):
-            raise ValueError("block_size must be 4, 8, 16 or 32")
+        if block_size not in (2, 4, 8, 16, 32, 64, 128):      # the reference's -L search set (src/2D-DCT.py:538)
+            raise ValueError("block_size must be a power of two in [2, 128]")
         if not (float(q) > 0):
             raise ValueError("q must be > 0")
         self.B = int(block_size)

@@ -28,7 +28,7 @@ int cuda_fail(cudaError_t e, const char* what) {
 }
 
 static bool make_geom(int H, int W, int B, Geom* g) {
-  if (H <= 0 || W <= 0 || (B != 4 && B != 8 && B != 16 && B != 32)) return false;
+  if (H <= 0 || W <= 0 || (B != 4 && B != 8 && B != 16 && B != 32 && !anyb_supported(B))) return false;
   g->H = H;
   g->W = W;
   g->Hp = (H + B - 1) / B * B;   // src/2D-DCT.py:208-209
@@ -44,7 +44,7 @@ static int check_common(const void* in, int n_frames, int H, int W, int B, doubl
                         unsigned flags, const double* weights, Geom* g) {
   if (!in) { set_error("input pointer is NULL"); return VCFB_E_ARG; }
   if (n_frames <= 0 || n_frames > 65535) { set_error("n_frames must be in [1, 65535]"); return VCFB_E_ARG; }
-  if (!make_geom(H, W, B, g)) { set_error("bad H/W or unsupported block size (supported B: 4, 8, 16, 32)"); return VCFB_E_ARG; }
+  if (!make_geom(H, W, B, g)) { set_error("bad H/W or unsupported block size (supported B: 2, 4, 8, 16, 32, 64, 128)"); return VCFB_E_ARG; }
   if (g->ny > 65535) { set_error("frame too tall for this block size"); return VCFB_E_ARG; }
   if (!(q > 0.0) || !isfinite(q)) { set_error("quantisation step q must be finite and > 0"); return VCFB_E_ARG; }
   if (color != VCFB_COLOR_YCOCG && color != VCFB_COLOR_YCRCB) { set_error("unknown colour transform"); return VCFB_E_ARG; }
@@ -110,6 +110,7 @@ int vcfb_encode_dev(const uint8_t* rgb, int n_frames, int H, int W, int B, doubl
   a.flags = flags;
   a.weights = weights;
   a.stats = reinterpret_cast<unsigned long long*>(stats);
+  if (anyb_supported(B)) return launch_encode_anyb(a, B, static_cast<cudaStream_t>(cuda_stream));
   if ((flags & VCFB_F_FAST) && B == 8 && !(flags & VCFB_F_FP64)) {
     // fast mode: tensor-core encoder; statistics, when asked for, by the streaming pass over the indices
     static const bool tc_off = getenv("VCFB_TC") && getenv("VCFB_TC")[0] == '0';
@@ -151,6 +152,7 @@ int vcfb_decode_dev(const uint8_t* idx, int n_frames, int H, int W, int B, doubl
   a.flags = flags;
   a.weights = weights;
   a.stats = reinterpret_cast<unsigned long long*>(stats);
+  if (anyb_supported(B)) return launch_decode_anyb(a, B, static_cast<cudaStream_t>(cuda_stream));
   if (!(flags & VCFB_F_SYNTH_F32)) {      // the upstream-variant decoder exists in the general kernel only
     rc = B == 16 ? launch_decode_fast16(a, static_cast<cudaStream_t>(cuda_stream))
                  : launch_decode_fast(a, B, static_cast<cudaStream_t>(cuda_stream));

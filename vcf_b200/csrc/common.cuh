@@ -55,6 +55,11 @@ void note_extra_launches(int n);      // launches that do not go through note_ke
 int launch_encode_general(const EncArgs& a, int B, cudaStream_t s);
 int launch_decode_general(const DecArgs& a, int B, cudaStream_t s);
 
+// block sizes 2, 64, 128 (the rest of the reference's -L search set): interpreted pocketfft programs (kernels_anyb.cu)
+bool anyb_supported(int B);
+int launch_encode_anyb(const EncArgs& a, int B, cudaStream_t s);
+int launch_decode_anyb(const DecArgs& a, int B, cudaStream_t s);
+
 // fast path (kernels_fast.cu): VCFB_E_UNSUPP means "not covered, use the general kernel"
 int launch_encode_fast(const EncArgs& a, int B, cudaStream_t s);
 int launch_decode_fast(const DecArgs& a, int B, cudaStream_t s);

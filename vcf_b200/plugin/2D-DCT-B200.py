@@ -41,10 +41,10 @@ default_block_size = 8
 default_CT = "YCoCg"
 perceptual_quantization = False
 disable_subbands = False
-SUPPORTED_B = (4, 8, 16, 32)
+SUPPORTED_B = (2, 4, 8, 16, 32, 64, 128)     # src/2D-DCT.py:538: 2**i, i = 1..7
 
 for _p in (parser.parser_encode, parser.parser_decode):
-    _p.add_argument("-B", "--block_size_DCT", type=parser.int_or_str, help=f"side of the square DCT blocks: 4, 8, 16 or 32 (default {default_block_size})", default=default_block_size)
+    _p.add_argument("-B", "--block_size_DCT", type=parser.int_or_str, help=f"side of the square DCT blocks: a power of two in [2, 128] (default {default_block_size})", default=default_block_size)
     _p.add_argument("-t", "--color_transform", type=parser.int_or_str, help=f"module providing the colour stage / base class (default {default_CT})", default=default_CT)
     _p.add_argument("-p", "--perceptual_quantization", action='store_true', help="weight the coefficients with the JPEG luma / chroma tables before quantising", default=perceptual_quantization)
     _p.add_argument("-x", "--disable_subbands", action='store_true', help="keep the coefficients in block order instead of grouping them by subband", default=disable_subbands)
@@ -185,9 +185,6 @@ class CoDec(CT.CoDec):
         self._check_image(img)
         img = np.ascontiguousarray(img)
         for block_size in [2**i for i in range(1, 8)]:
-            if block_size not in SUPPORTED_B:
-                logging.warning(f"block_size={block_size} skipped (GPU path supports {SUPPORTED_B})")
-                continue
             if img.shape[0] % block_size or img.shape[1] % block_size:
                 logging.warning(f"block_size={block_size} skipped (the reference applies no padding here)")
                 continue
