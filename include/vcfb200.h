@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define VCFB_VERSION 130 /* 0.3.0: + VCFB_F_SYNTH_F32; 0.2.0: + vcfb_deflate_dev, vcfb_deflate_bound, vcfb_deflate_workspace, vcfb_crc32_dev, vcfb_adler32_dev (0.1.1: vcfb_launch_count, motion estimation) */
+#define VCFB_VERSION 140 /* 0.4.0: + vcfb_rd_sweep_dev, VCFB_F_NOWRAP, block sizes 2 / 64 / 128; 0.3.0: + VCFB_F_SYNTH_F32; 0.2.0: + vcfb_deflate_dev, vcfb_deflate_bound, vcfb_deflate_workspace, vcfb_crc32_dev, vcfb_adler32_dev (0.1.1: vcfb_launch_count, motion estimation) */
 
 /* error codes */
 #define VCFB_OK 0
@@ -75,6 +75,11 @@ extern "C" {
                                  only at rounding boundaries.  Applies to B = 8, YCoCg, subbands,
                                  q = 2^k >= 8; any other request is served by the bit-exact encoder.
                                  Decode: ignored (float32 decode IS the fast mode). */
+
+#define VCFB_F_NOWRAP 128u    /* vcfb_rd_sweep_dev only: dequantise the quantiser's own indices, before they are
+                                 narrowed to uint8 -- the in-process loop of optimize_block_size
+                                 (src/2D-DCT.py:560-566).  Without it: the indices a decoder reads back from the
+                                 code-stream (wrapped to uint8 :361, int16 arithmetic :398-410). */
 
 #define VCFB_F_HIST 16u       /* statistics: also accumulate the 3 x 256 histogram of the indices
                                  (one shared-memory atomic per sample; off = only the sums) */
@@ -143,6 +148,20 @@ int vcfb_decode_dev(const uint8_t* idx, int n_frames, int H, int W, int B, doubl
                     int color, unsigned flags, const double* weights,
                     uint8_t* rgb_out, void* y_out, const uint8_t* original,
                     int64_t* stats, void* cuda_stream);
+
+/* Fused rate/distortion sweep: every quantisation step of one block size in ONE pass over
+ * the frames -- forward transform once, then per step quantise / dequantise / the float64 decode chain / SSE
+ * against the input, all on chip; nothing but statistics is written (3 B/pixel of HBM traffic per block size).
+ * Replaces the body of the loop of src/2D-DCT.py:533-579 (optimize_block_size) and the encode + decode + RDE
+ * runs per point of src/RDE.py:68-118; the numbers are those vcfb_encode_dev (float32, bit-exact) followed by
+ * vcfb_decode_dev (VCFB_F_FP64, bit-exact) with `original` accumulate, step for step.
+ * q_steps   n_steps quantisation steps (host array), n_steps <= VCFB_RD_MAX_STEPS
+ * flags     VCFB_F_HIST, VCFB_F_NOWRAP; no perceptual weights (the reference's loop applies none)
+ * stats     n_steps x VCFB_STAT_LEN int64 on the device, zeroed by the caller: row i is the statistics vector of
+ *           q_steps[i] (SSE, NSAMPLES, SUMDIFF of the decoded image; NONZERO, SUMABS, NINDICES, HIST of the indices) */
+#define VCFB_RD_MAX_STEPS 16
+int vcfb_rd_sweep_dev(const uint8_t* rgb, int n_frames, int H, int W, int B, const double* q_steps, int n_steps,
+                      int color, unsigned flags, int64_t* stats, void* cuda_stream);
 
 /* Stand-alone colour codecs: the reference's colour stages run as codecs of their own
  * (`python YCoCg.py encode`, `python YCrCb.py encode`), colour transform + deadzone

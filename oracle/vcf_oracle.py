@@ -436,6 +436,31 @@ def rmse(a: np.ndarray, b: np.ndarray):
     return np.sqrt((d ** 2).mean())
 
 
+def optimize_block_size_point(img_u8: np.ndarray, B: int, q, *, color: str = "YCoCg"):
+    """One iteration of the loop of src/2D-DCT.py:538-578 (optimize_block_size), returning
+    ``(k_u8, y_u8, RMSE)``: the array handed to ``self.compress`` (:559), the reconstruction (:571) and
+    the distortion the reference forms (:574) -- between the image STILL SHIFTED by 128 (:536-537) and
+    the un-shifted reconstruction.  Differences from encode_fn + decode_fn that a drop-in must keep: no
+    padding (:536; shapes must be multiples of B), no perceptual scaling, and the dequantiser receives the
+    quantiser's own integer indices (:565-566) -- never narrowed to uint8, never int16."""
+    img = img_u8.astype(np.float32)                              # :536
+    img -= OFFSET                                                # :537
+    ct = ycocg_from_rgb(img) if color == "YCoCg" else ycrcb_from_rgb_float(img)   # :540
+    coef = analyze_image(ct, B, B)                               # :541
+    decom = get_subbands(coef, B, B)                             # :542
+    Q = DeadzoneQuantizer(q)
+    k = Q.encode(decom)                                          # :556
+    k += OFFSET                                                  # :557
+    k_u8 = k.astype(np.uint8)                                    # :563 (argument of compress)
+    k -= OFFSET                                                  # :566
+    y = Q.decode(k)                                              # :568 (int64 * q)
+    ct_y = synthesize_image(get_blocks(y, B, B), B, B)           # :569-570 (float64)
+    y = ycocg_to_rgb(ct_y) if color == "YCoCg" else ycrcb_to_rgb_float(ct_y)      # :571
+    y += OFFSET                                                  # :572
+    y = np.clip(y, 0, 255).astype(np.uint8)                      # :573
+    return k_u8, y, rmse(img, y)                                 # :574
+
+
 def sse_int(a_u8: np.ndarray, b_u8: np.ndarray) -> int:
     """Exact integer sum of squared errors (what the GPU statistic kernel
     accumulates); RMSE = sqrt(SSE / N) up to float32 rounding of the mean."""

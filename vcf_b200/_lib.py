@@ -17,7 +17,8 @@ STAT_NONZERO, STAT_SUMABS, STAT_NINDICES, STAT_SUMDIFF, STAT_HIST = 4, 5, 6, 7, 
 STAT_LEN = 8 + 3 * 256
 
 COLOR_YCOCG, COLOR_YCRCB = 0, 1
-F_NO_SUBBANDS, F_PERCEPTUAL, F_FP64, F_CONTRACT, F_HIST, F_SYNTH_F32, F_FAST = 1, 2, 4, 8, 16, 32, 64
+F_NO_SUBBANDS, F_PERCEPTUAL, F_FP64, F_CONTRACT, F_HIST, F_SYNTH_F32, F_FAST, F_NOWRAP = 1, 2, 4, 8, 16, 32, 64, 128
+RD_MAX_STEPS = 16
 
 
 class VcfbError(RuntimeError):
@@ -48,6 +49,8 @@ def lib():
     L.vcfb_encode_dev.restype = i
     L.vcfb_decode_dev.argtypes = [vp, i, i, i, i, d, i, u, vp, vp, vp, vp, vp, vp]
     L.vcfb_decode_dev.restype = i
+    L.vcfb_rd_sweep_dev.argtypes = [vp, i, i, i, i, C.POINTER(d), i, i, u, vp, vp]
+    L.vcfb_rd_sweep_dev.restype = i
     L.vcfb_ctx_create.argtypes = [i, C.POINTER(vp)]
     L.vcfb_ctx_create.restype = i
     L.vcfb_ctx_destroy.argtypes = [vp]

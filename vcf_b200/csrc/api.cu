@@ -161,6 +161,26 @@ int vcfb_decode_dev(const uint8_t* idx, int n_frames, int H, int W, int B, doubl
   return launch_decode_general(a, B, static_cast<cudaStream_t>(cuda_stream));
 }
 
+int vcfb_rd_sweep_dev(const uint8_t* rgb, int n_frames, int H, int W, int B, const double* q_steps, int n_steps,
+                      int color, unsigned flags, int64_t* stats, void* cuda_stream) {
+  Geom g;
+  if (!q_steps || n_steps < 1 || n_steps > VCFB_RD_MAX_STEPS) { set_error("n_steps must be in [1, VCFB_RD_MAX_STEPS]"); return VCFB_E_ARG; }
+  if (!stats) { set_error("stats is NULL"); return VCFB_E_ARG; }
+  if (flags & ~(VCFB_F_HIST | VCFB_F_NOWRAP)) { set_error("vcfb_rd_sweep_dev takes VCFB_F_HIST and VCFB_F_NOWRAP only"); return VCFB_E_ARG; }
+  for (int i = 0; i < n_steps; ++i) {
+    int rc = check_common(rgb, n_frames, H, W, B, q_steps[i], color, 0, nullptr, &g);
+    if (rc) return rc;
+    if (!(flags & VCFB_F_NOWRAP) && q_steps[i] == floor(q_steps[i]) && q_steps[i] >= 32768.0) {
+      set_error("integral quantisation step does not fit int16: the reference's dequantiser raises OverflowError");
+      return VCFB_E_ARG;
+    }
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  unsigned long long* st = reinterpret_cast<unsigned long long*>(stats);
+  if (anyb_supported(B)) return launch_rd_sweep_anyb(rgb, g, n_frames, B, q_steps, n_steps, color, flags, st, s);
+  return launch_rd_sweep(rgb, g, n_frames, B, q_steps, n_steps, color, flags, st, s);
+}
+
 int vcfb_color_encode_dev(const uint8_t* rgb, long long n_pixels, double q, int color, uint16_t* k_out,
                           void* cuda_stream) {
   if (!rgb || !k_out) { set_error("NULL pointer"); return VCFB_E_ARG; }

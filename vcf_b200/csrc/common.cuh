@@ -60,6 +60,12 @@ bool anyb_supported(int B);
 int launch_encode_anyb(const EncArgs& a, int B, cudaStream_t s);
 int launch_decode_anyb(const DecArgs& a, int B, cudaStream_t s);
 
+// fused rate/distortion sweep (kernels_rd.cu: B in {4, 8, 16, 32}; kernels_anyb.cu: 2, 64, 128)
+int launch_rd_sweep(const uint8_t* rgb, const Geom& g, int n_frames, int B, const double* qs, int nq, int color,
+                    unsigned flags, unsigned long long* stats, cudaStream_t s);
+int launch_rd_sweep_anyb(const uint8_t* rgb, const Geom& g, int n_frames, int B, const double* qs, int nq, int color,
+                         unsigned flags, unsigned long long* stats, cudaStream_t s);
+
 // fast path (kernels_fast.cu): VCFB_E_UNSUPP means "not covered, use the general kernel"
 int launch_encode_fast(const EncArgs& a, int B, cudaStream_t s);
 int launch_decode_fast(const DecArgs& a, int B, cudaStream_t s);

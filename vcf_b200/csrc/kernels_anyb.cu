@@ -14,6 +14,9 @@
 //   decode:  anyb_dec_cols   (channel, coefficient column, block row): dequantise, inverse DCT (axis 0)
 //            anyb_dec_rows   (channel, row, block): inverse DCT (axis 1), in place
 //            anyb_dec_pixels (pixel): to_RGB, +128, float output, clip, truncate, SSE
+#include <math.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "exact_ops.cuh"
 #include "dag_programs.inc"
@@ -108,7 +111,8 @@ __global__ void __launch_bounds__(NT) anyb_enc_cols(const EncArgs a, int B, int 
   for (int u = 0; u < B; ++u) F[(size_t(by) * B + u) * g.Wp + x] = dag_out<T>(p, s, u);
 }
 
-template <typename T, bool EXACT>
+// KEEP: the coefficients go back into the plane (fused rate/distortion sweep) instead of being quantised
+template <typename T, bool EXACT, bool KEEP = false>
 __global__ void __launch_bounds__(NT) anyb_enc_rows(const EncArgs a, int B, int f, void* scratch) {
   using O = Ops<T, EXACT>;
   const Geom g = a.g;
@@ -126,9 +130,13 @@ __global__ void __launch_bounds__(NT) anyb_enc_rows(const EncArgs a, int B, int 
     const bool percep = (a.flags & VCFB_F_PERCEPTUAL) != 0;
     const DagProgram p = dag_program(B, false);
     T s[DAGP_MAX_SLOTS];
-    const T* src = plane<T>(scratch, g, c) + size_t(y) * g.Wp + size_t(bx) * B;
+    T* src = plane<T>(scratch, g, c) + size_t(y) * g.Wp + size_t(bx) * B;
     for (int i = 0; i < B; ++i) s[i] = src[i];
     dag_run<T, EXACT>(p, s);
+    if (KEEP) {
+      for (int i = 0; i < B; ++i) src[i] = dag_out<T>(p, s, i);
+      return;
+    }
     const T q = T(a.q), inv_q = T(a.inv_q);
     const double* wt = percep ? a.weights + (c ? B * B : 0) + u * B : nullptr;
     for (int i = 0; i < B; ++i) {
@@ -154,7 +162,7 @@ __global__ void __launch_bounds__(NT) anyb_enc_rows(const EncArgs a, int B, int 
       }
     }
   }
-  if (do_stats) {
+  if (do_stats && !KEEP) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       nz += __shfl_xor_sync(0xffffffffu, nz, o);
@@ -168,7 +176,42 @@ __global__ void __launch_bounds__(NT) anyb_enc_rows(const EncArgs a, int B, int 
   }
 }
 
-template <typename T, bool EXACT>
+// Fused sweep, one step: quantise the float32 coefficient plane (block layout), statistics of the indices,
+// dequantise into the float64 plane.  Semantics of kernels_rd.cu (wrapped / VCFB_F_NOWRAP).
+__global__ void __launch_bounds__(NT) anyb_rd_quant(const float* coef, double* deq, long long n_per_channel, double qd,
+                                                    int q_pow2, int q_int, unsigned flags, unsigned long long* stats) {
+  using OF = Ops<float, true>;
+  const long long item = (long long)blockIdx.x * NT + threadIdx.x;
+  unsigned nz = 0, sabs = 0;
+  if (item < 3 * n_per_channel) {
+    const int c = int(item / n_per_channel);
+    const float v = coef[item];
+    const float tq = q_pow2 ? OF::mul(v, float(1.0 / qd)) : OF::div(v, float(qd));
+    const int k = __float2int_rz(tq);
+    const unsigned byte = unsigned(k + 128) & 255u;
+    const int k8 = int(byte) - 128;
+    nz = (k8 != 0);
+    sabs = unsigned(k8 < 0 ? -k8 : k8);
+    if (flags & VCFB_F_HIST) atomicAdd(stats + VCFB_STAT_HIST + c * 256 + byte, 1ULL);
+    double y;
+    if (flags & VCFB_F_NOWRAP) y = q_int ? double((long long)k * q_int) : double(k) * qd;
+    else y = q_int ? double(int(short(k8 * q_int))) : double(k8) * qd;
+    deq[item] = y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    nz += __shfl_xor_sync(0xffffffffu, nz, o);
+    sabs += __shfl_xor_sync(0xffffffffu, sabs, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (nz) atomicAdd(stats + VCFB_STAT_NONZERO, (unsigned long long)nz);
+    if (sabs) atomicAdd(stats + VCFB_STAT_SUMABS, (unsigned long long)sabs);
+  }
+  if (item == 0) atomicAdd(stats + VCFB_STAT_NINDICES, (unsigned long long)(3 * n_per_channel));
+}
+
+// FROM_PLANE: the dequantised values are already in the plane (fused sweep), block layout
+template <typename T, bool EXACT, bool FROM_PLANE = false>
 __global__ void __launch_bounds__(NT) anyb_dec_cols(const DecArgs a, int B, int f, void* scratch) {
   const Geom g = a.g;
   const long long item = (long long)blockIdx.x * NT + threadIdx.x;
@@ -182,6 +225,10 @@ __global__ void __launch_bounds__(NT) anyb_dec_cols(const DecArgs a, int B, int 
   const bool percep = (a.flags & VCFB_F_PERCEPTUAL) != 0;
   const DagProgram p = dag_program(B, true);
   T s[DAGP_MAX_SLOTS];
+  if (FROM_PLANE) {
+    const T* src = plane<T>(scratch, g, c) + size_t(by) * B * g.Wp + x;
+    for (int u = 0; u < B; ++u) s[u] = src[size_t(u) * g.Wp];
+  } else
   for (int u = 0; u < B; ++u) {
     size_t row, col;
     if (nosub) {
@@ -343,6 +390,48 @@ int run_decode(const DecArgs& a, int B, cudaStream_t s) {
 }
 
 }  // namespace
+
+// Fused rate/distortion sweep for the interpreted sizes: the forward transform once, then per step
+// quantise / dequantise / inverse transform / SSE.  stats: nq x VCFB_STAT_LEN.
+int launch_rd_sweep_anyb(const uint8_t* rgb, const Geom& g, int n_frames, int B, const double* qs, int nq, int color,
+                         unsigned flags, unsigned long long* stats, cudaStream_t s) {
+  const size_t npl = size_t(g.Hp) * g.Wp;
+  void *fplane = nullptr, *dplane = nullptr;
+  cudaError_t e = cudaMallocAsync(&fplane, 3 * npl * sizeof(float), s);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMallocAsync(any-B scratch)");
+  e = cudaMallocAsync(&dplane, 3 * npl * sizeof(double), s);
+  if (e != cudaSuccess) { cudaFreeAsync(fplane, s); return cuda_fail(e, "cudaMallocAsync(any-B scratch)"); }
+  EncArgs ea;
+  memset(&ea, 0, sizeof(ea));
+  ea.rgb = rgb; ea.g = g; ea.n_frames = n_frames; ea.color = color; ea.flags = flags & ~VCFB_F_NOWRAP;
+  DecArgs da;
+  memset(&da, 0, sizeof(da));
+  da.g = g; da.n_frames = n_frames; da.color = color; da.flags = VCFB_F_FP64; da.original = rgb;
+  for (int f = 0; f < n_frames; ++f) {
+    note_kernel("rd_sweep_anyb");
+    anyb_enc_cols<float, true><<<blocks_for(3LL * g.ny * g.Wp), NT, 0, s>>>(ea, B, f, fplane);
+    anyb_enc_rows<float, true, true><<<blocks_for(3LL * g.Hp * g.nx), NT, 0, s>>>(ea, B, f, fplane);
+    note_extra_launches(1);
+    for (int qi = 0; qi < nq; ++qi) {
+      const double q = qs[qi];
+      int e2;
+      const int pow2 = frexp(q, &e2) == 0.5;
+      const int q_int = (q == floor(q) && q < 32768.0) ? int(q) : 0;
+      da.stats = stats + size_t(qi) * VCFB_STAT_LEN;
+      anyb_rd_quant<<<blocks_for(3LL * npl), NT, 0, s>>>(static_cast<const float*>(fplane), static_cast<double*>(dplane),
+                                                        (long long)npl, q, pow2, q_int, flags, da.stats);
+      anyb_dec_cols<double, true, true><<<blocks_for(3LL * g.ny * g.Wp), NT, 0, s>>>(da, B, f, dplane);
+      anyb_dec_rows<double, true><<<blocks_for(3LL * g.Hp * g.nx), NT, 0, s>>>(da, B, dplane);
+      anyb_dec_pixels<double, true><<<blocks_for((long long)g.H * g.W), NT, 0, s>>>(da, f, dplane);
+      note_extra_launches(4);
+    }
+  }
+  e = cudaGetLastError();
+  cudaFreeAsync(fplane, s);
+  cudaFreeAsync(dplane, s);
+  if (e != cudaSuccess) return cuda_fail(e, "any-B rd sweep launch");
+  return VCFB_OK;
+}
 
 bool anyb_supported(int B) { return B == 2 || B == 64 || B == 128; }
 

@@ -16,7 +16,51 @@ from typing import Callable, Iterable, Optional
 
 import numpy as np
 
-from .codec import Codec, _is_torch, stats_dict
+from . import _lib
+from .codec import Codec, _COLORS, _is_torch, stats_dict
+
+
+def rd_stats_fused(frames, block_size: int, qs, color: str = "YCoCg", nowrap: bool = False, hist: bool = True):
+    """Statistics vectors of every step in ``qs`` for one block size from ONE pass over ``frames``
+    (vcfb_rd_sweep_dev, csrc/kernels_rd.cu): the forward transform runs once, each step is quantised,
+    dequantised and decoded on chip, nothing but the int64 statistics is written.  Row i equals what
+    ``Codec(B, qs[i]).encode(stats)`` + ``Codec(B, qs[i], fp64=True).decode(original, stats)`` accumulate.
+
+    nowrap: the dequantiser sees the quantiser's own indices, not the ones wrapped to uint8 -- the
+    in-process loop of src/2D-DCT.py:533-579 (optimize_block_size).
+    frames: CUDA uint8 tensor (n,H,W,3)|(H,W,3) (a numpy array is uploaded).  Returns an int64 tensor
+    (len(qs), STAT_LEN) on the device."""
+    import ctypes as C
+    import torch
+    L = _lib.lib()
+    if L.vcfb_device_count() < 1:
+        raise _lib.VcfbError("no CUDA device: vcf_b200 has no CPU fallback")
+    x = frames if _is_torch(frames) else torch.from_numpy(np.ascontiguousarray(frames)).cuda()
+    if x.ndim == 3:
+        x = x[None]
+    if x.ndim != 4 or x.shape[-1] != 3 or x.dtype != torch.uint8 or not x.is_cuda:
+        raise ValueError("frames must be uint8 (n,H,W,3) or (H,W,3)")
+    x = x.contiguous()
+    qs = [float(q) for q in qs]
+    out = torch.zeros((len(qs), _lib.STAT_LEN), dtype=torch.int64, device=x.device)
+    flags = (_lib.F_HIST if hist else 0) | (_lib.F_NOWRAP if nowrap else 0)
+    n, H, W, _ = x.shape
+    with torch.cuda.device(x.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        for i in range(0, len(qs), _lib.RD_MAX_STEPS):
+            part = qs[i:i + _lib.RD_MAX_STEPS]
+            arr = (C.c_double * len(part))(*part)
+            _lib.check(L.vcfb_rd_sweep_dev(x.data_ptr(), n, H, W, int(block_size), arr, len(part), _COLORS[color],
+                                           flags, out[i:].data_ptr(), stream))
+    return out
+
+
+def _point(B, q, st):
+    npx = st["nsamples"] // 3
+    res = dict(B=B, q=q, rmse=st["rmse"], psnr=st["psnr"], sse=int(st["sse"].sum()), nonzero=st["nonzero"])
+    if "entropy_bits" in st:
+        res["bpp_entropy"] = st["entropy_bits"] / npx
+    return res
 
 
 def rd_point(frames, block_size: int, q, compress: Optional[Callable] = None, **codec_kw) -> dict:
@@ -55,9 +99,24 @@ def rd_point(frames, block_size: int, q, compress: Optional[Callable] = None, **
 
 
 def rd_sweep(frames, block_sizes: Iterable[int] = (4, 8, 16, 32), qs: Iterable = (4, 8, 12, 16, 24, 32, 48, 64),
-             compress: Optional[Callable] = None, **codec_kw):
-    """BASELINE config 3: every (B, q) point of a frame (or batch) kept on the device."""
-    return [rd_point(frames, B, q, compress, **codec_kw) for B in block_sizes for q in qs]
+             compress: Optional[Callable] = None, fused: bool = True, **codec_kw):
+    """BASELINE config 3: every (B, q) point of a frame (or batch) kept on the device.
+
+    fused (default): one pass per block size evaluates all steps (``rd_stats_fused``) -- same numbers as the
+    per-point path, which remains for requests the fused kernel does not take (perceptual weights, a real
+    entropy coder through ``compress``, float64 / contracted forward transforms)."""
+    qs = list(qs)
+    plain = compress is None and not any(codec_kw.get(k) for k in ("perceptual", "fp64", "contract", "fast",
+                                                                   "disable_subbands", "synth_f32"))
+    if not (fused and plain):
+        return [rd_point(frames, B, q, compress, **codec_kw) for B in block_sizes for q in qs]
+    out = []
+    tables = [(B, rd_stats_fused(frames, B, qs, color=codec_kw.get("color", "YCoCg"), hist=codec_kw.get("hist", True)))
+              for B in block_sizes]          # all launches first, one synchronising copy at the end
+    for B, t in tables:
+        t = t.cpu().numpy()
+        out += [_point(B, q, stats_dict(t[i])) for i, q in enumerate(qs)]
+    return out
 
 
 def best_block_size(frame, q, Lambda: float, compress: Callable, block_sizes=(4, 8, 16, 32)):
