@@ -67,14 +67,32 @@ template <int B> struct RdLayout {
   static constexpr int SMEM = RAW_BYTES + G_BYTES + 3 * 256 * 4 + MAXQ * 8 * 4 + 64;
 };
 
-__device__ __forceinline__ unsigned warp_sum(unsigned v) {
+__device__ __forceinline__ unsigned warp_sum(unsigned v) { return __reduce_add_sync(0xffffffffu, v); }   // one REDUX
+
+// Phase A of one step for one row of B coefficients, with everything that depends only on the step a
+// compile-time constant (the uniform branches otherwise sit inside the unrolled element loop).
+template <int B, bool POW2, bool QINT, bool NOWRAP>
+__device__ __forceinline__ void quantise_row(const float (&coef)[B], float q, float inv_q, int q_int, double qd,
+                                             double* dst, unsigned* hist_c, bool do_hist, unsigned& nz, unsigned& sabs) {
+  using OF = Ops<float, true>;
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
+  for (int i = 0; i < B; ++i) {
+    const float tq = POW2 ? OF::mul(coef[i], inv_q) : OF::div(coef[i], q);   // src/deadzone.py:98
+    const int k = __float2int_rz(tq);                       // truncation = dead zone
+    const unsigned byte = unsigned(k + 128) & 255u;         // src/2D-DCT.py:348,:361 (wraps)
+    const int k8 = int(byte) - 128;                         // what a decoder reads back (:398,:402)
+    nz += (k8 != 0);
+    sabs += unsigned(abs(k8));
+    if (do_hist && k8 != 0) atomicAdd(&hist_c[byte], 1u);   // bin 128 is counted through nz
+    double y;
+    if (NOWRAP) y = QINT ? double((long long)k * q_int) : double(k) * qd;          // :565-568 (int64 indices)
+    else y = QINT ? double(int(short(k8 * q_int))) : double(k8) * qd;              // int16 * python int stays int16
+    dst[i] = y;
+  }
 }
 
 template <int B>
-__global__ void __launch_bounds__(RdLayout<B>::NT) rd_sweep_kernel(const RdArgs a) {
+__global__ void __launch_bounds__(RdLayout<B>::NT, 3) rd_sweep_kernel(const RdArgs a) {
   using L = RdLayout<B>;
   using OF = Ops<float, true>;
   using OD = Ops<double, true>;
@@ -176,30 +194,34 @@ __global__ void __launch_bounds__(RdLayout<B>::NT) rd_sweep_kernel(const RdArgs 
     {
       const float q = float(a.q[qi]), inv_q = a.inv_q[qi];
       const int q_int = a.q_int[qi];
+      const double qd = a.q[qi];
       const bool pow2 = a.q_pow2[qi] != 0;
       unsigned nz = 0, sabs = 0;
       double* dst = G + (c * B + u) * GP + bx * B;
-      if (live) {
-#pragma unroll
-        for (int i = 0; i < B; ++i) {
-          const float tq = pow2 ? OF::mul(coef[i], inv_q) : OF::div(coef[i], q);
-          const int k = __float2int_rz(tq);                       // truncation = dead zone
-          const unsigned byte = unsigned(k + 128) & 255u;         // src/2D-DCT.py:348,:361 (wraps)
-          const int k8 = int(byte) - 128;                         // what a decoder reads back (:398,:402)
-          nz += (k8 != 0);
-          sabs += unsigned(k8 < 0 ? -k8 : k8);
-          if (do_hist) atomicAdd(&shist[c * 256 + byte], 1u);
-          double y;
-          if (nowrap) y = q_int ? double((long long)k * q_int) : double(k) * a.q[qi];
-          else y = q_int ? double(int(short(k8 * q_int))) : double(k8) * a.q[qi];   // int16 * python int stays int16
-          dst[i] = y;
-        }
+      unsigned* hc = shist + c * 256;
+      // (lanes of blocks beyond the frame's right edge hold zero coefficients: they store zeros into their own
+      //  part of the tile and count nothing)
+#define VCFB_RD_ROW(P2, QI, NW) quantise_row<B, P2, QI, NW>(coef, q, inv_q, q_int, qd, dst, hc, do_hist, nz, sabs)
+      if (nowrap) {
+        if (pow2) { if (q_int) VCFB_RD_ROW(true, true, true); else VCFB_RD_ROW(true, false, true); }
+        else      { if (q_int) VCFB_RD_ROW(false, true, true); else VCFB_RD_ROW(false, false, true); }
+      } else {
+        if (pow2) { if (q_int) VCFB_RD_ROW(true, true, false); else VCFB_RD_ROW(true, false, false); }
+        else      { if (q_int) VCFB_RD_ROW(false, true, false); else VCFB_RD_ROW(false, false, false); }
       }
-      nz = warp_sum(nz);
-      sabs = warp_sum(sabs);
+#undef VCFB_RD_ROW
+      // nz <= 32 and sabs <= 128 * 32 per lane: one reduction carries both; c is warp-uniform (TW is a multiple of 32)
+      const unsigned packed = warp_sum((nz << 20) | sabs);
+      const unsigned nlive = unsigned(__popc(__ballot_sync(0xffffffffu, live)));
       if ((tid & 31) == 0) {
+        nz = packed >> 20;
+        sabs = packed & 0xFFFFFu;
         if (nz) atomicAdd(&sacc[qi * 8 + 0], nz);
         if (sabs) atomicAdd(&sacc[qi * 8 + 1], sabs);
+        if (do_hist) {
+          const unsigned zeros = nlive * B - nz;
+          if (zeros) atomicAdd(&hc[128], zeros);
+        }
       }
     }
     __syncthreads();
@@ -241,40 +263,45 @@ __global__ void __launch_bounds__(RdLayout<B>::NT) rd_sweep_kernel(const RdArgs 
     __syncthreads();
 
     // ---- P: to_RGB, +128, truncate, clip (:449-466); SSE against the input (src/RDE.py:41-49) ----
+    // thread = pixel column t, rows c, c + 3, c + 6, ...
     {
       unsigned sse[3] = {0, 0, 0};
       int sdiff = 0;
-      for (int p = tid; p < B * TW; p += NT) {
-        const int r = p / TW, x = p - r * TW;
-        const int gy = by * B + r - g.top;
-        const int gx = x0 + x - g.left;
-        if (x >= nbx * B || gy < 0 || gy >= g.H || gx < 0 || gx >= g.W) continue;
-        const double c0 = G[(0 * B + r) * GP + x], c1 = G[(1 * B + r) * GP + x], c2 = G[(2 * B + r) * GP + x];
-        double R, Gv, Bv;
-        if (a.color == VCFB_COLOR_YCOCG) {   // Y + Co - Cg ; Y + Cg ; Y - Co - Cg, left to right
-          R = OD::sub(OD::add(c0, c1), c2);
-          Gv = OD::add(c0, c2);
-          Bv = OD::sub(OD::sub(c0, c1), c2);
-        } else {                             // oracle ycrcb_to_rgb_float
-          R = OD::add(c0, OD::mul(c1, 1.403));
-          Gv = OD::add(OD::add(c0, OD::mul(c1, -0.714)), OD::mul(c2, -0.344));
-          Bv = OD::add(c0, OD::mul(c2, 1.773));
-        }
-        const int v[3] = {min(max(__double2int_rz(OD::add(R, 128.0)), 0), 255),
-                          min(max(__double2int_rz(OD::add(Gv, 128.0)), 0), 255),
-                          min(max(__double2int_rz(OD::add(Bv, 128.0)), 0), 255)};
-        const uint8_t* px = raw + r * RAWP + x * 3;
+      const int x = t;
+      const int gx = x0 + x - g.left;
+      if (x < nbx * B && gx >= 0 && gx < g.W) {
 #pragma unroll
-        for (int k = 0; k < 3; ++k) {
-          const int d = int(px[k]) - v[k];
-          sse[k] += unsigned(d * d);
-          sdiff += d;
+        for (int j = 0; j < (B + 2) / 3; ++j) {
+          const int r = c + 3 * j;
+          const int gy = by * B + r - g.top;
+          if (r >= B || gy < 0 || gy >= g.H) continue;
+          const double c0 = G[(0 * B + r) * GP + x], c1 = G[(1 * B + r) * GP + x], c2 = G[(2 * B + r) * GP + x];
+          double R, Gv, Bv;
+          if (a.color == VCFB_COLOR_YCOCG) {   // Y + Co - Cg ; Y + Cg ; Y - Co - Cg, left to right
+            R = OD::sub(OD::add(c0, c1), c2);
+            Gv = OD::add(c0, c2);
+            Bv = OD::sub(OD::sub(c0, c1), c2);
+          } else {                             // oracle ycrcb_to_rgb_float
+            R = OD::add(c0, OD::mul(c1, 1.403));
+            Gv = OD::add(OD::add(c0, OD::mul(c1, -0.714)), OD::mul(c2, -0.344));
+            Bv = OD::add(c0, OD::mul(c2, 1.773));
+          }
+          const int v[3] = {min(max(__double2int_rz(OD::add(R, 128.0)), 0), 255),
+                            min(max(__double2int_rz(OD::add(Gv, 128.0)), 0), 255),
+                            min(max(__double2int_rz(OD::add(Bv, 128.0)), 0), 255)};
+          const uint8_t* px = raw + r * RAWP + x * 3;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) {
+            const int d = int(px[k]) - v[k];
+            sse[k] += unsigned(d * d);
+            sdiff += d;
+          }
         }
       }
 #pragma unroll
       for (int k = 0; k < 3; ++k) {
-        const unsigned s = warp_sum(sse[k]);
-        if ((tid & 31) == 0 && s) atomicAdd(&sacc[qi * 8 + 2 + k], s);
+        const unsigned sv = warp_sum(sse[k]);
+        if ((tid & 31) == 0 && sv) atomicAdd(&sacc[qi * 8 + 2 + k], sv);
       }
       const unsigned sd = warp_sum(unsigned(sdiff));             // two's complement sum
       if ((tid & 31) == 0 && sd) atomicAdd(&sacc[qi * 8 + 5], sd);
@@ -310,6 +337,7 @@ int launch_rd(const RdArgs& a, cudaStream_t s) {
   using L = RdLayout<B>;
   auto kern = rd_sweep_kernel<B>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::SMEM);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(rd_sweep)");
   dim3 grid((a.g.Wp + L::TW - 1) / L::TW, a.g.ny, a.n_frames);
   note_kernel("rd_sweep");
