@@ -93,11 +93,9 @@ def test_iii_style_per_frame_loop_and_block_size_optimiser():
     assert r.returncode == 0, r.stderr[-2000:]
     best, bestJ = None, 1e18
     for B in (2, 4, 8, 16, 32, 64):
-        k = O.encode_array(img, B, 16)
+        k, y, rm = O.optimize_block_size_point(img, B, 16)     # the reference's loop body, :538-574
         b = io.BytesIO()
         np.savez_compressed(file=b, a=k)
-        y = O.decode_array(k, img.shape, B, 16)
-        rm = float(np.sqrt(np.mean(((img.astype(np.float64) - 128) - y) ** 2)))
         J = len(b.getvalue()) + 50.0 * rm
         if J < bestJ:
             best, bestJ = B, J

@@ -36,6 +36,8 @@ with open("/tmp/description.txt", 'w') as f:   # handshake read by src/parser.py
 import parser  # noqa: E402  (reference src/parser.py)
 
 from vcf_b200 import Codec  # noqa: E402
+from vcf_b200.codec import stats_dict  # noqa: E402
+from vcf_b200.rd import rd_stats_fused  # noqa: E402
 
 default_block_size = 8
 default_CT = "YCoCg"
@@ -188,12 +190,14 @@ class CoDec(CT.CoDec):
             if img.shape[0] % block_size or img.shape[1] % block_size:
                 logging.warning(f"block_size={block_size} skipped (the reference applies no padding here)")
                 continue
-            enc, dec = self._codec(block_size), self._codec(block_size, decode=True)
+            enc = Codec(block_size=block_size, q=self.QSS)     # the loop knows neither -p nor -x (:540-556)
             decom_k = enc.encode(img)
             decom_k_bytes = self.compress(decom_k)
             decom_k_bytes.seek(0)
             rate = len(decom_k_bytes.read())
-            _, st = dec.decode(decom_k, img.shape[:2], original=img, stats=True)
+            # :565-573 -- the loop dequantises the quantiser's own indices (never narrowed to uint8, no int16,
+            # no perceptual weights): the fused sweep kernel with VCFB_F_NOWRAP, one step
+            st = stats_dict(rd_stats_fused(img, block_size, [self.QSS], nowrap=True, hist=False)[0].cpu().numpy())
             n = st["nsamples"]
             se = float(st["sse"].sum()) - 256.0 * st["sumdiff"] + 16384.0 * n   # sum((img-128) - y)^2
             RMSE = float(np.sqrt(se / n))
