@@ -373,6 +373,59 @@ def timed_steps(cx: Ctx, step, steps, warmup, sampler=None, finalize=None):
     return ms, enc_ms, dec_ms, launches, (t0w, t1w)
 
 
+def measure_rd_sweep(cx: Ctx, a, frames_per_gpu: int = 1):
+    """BASELINE configs[2]: the rate/distortion sweep B in {4,8,16,32} x 8 steps over a 4K frame, through the
+    fused kernel (one pass per block size, vcfb_rd_sweep_dev) -- every rank sweeps its own frame(s) and the
+    4 x 8 statistics vectors are summed over the ranks by one NCCL all-reduce per sweep (asynchronous, waited
+    for inside the timed region).  `value` counts pixels x (B, q) points per second, whole job."""
+    from vcf_b200 import _lib
+    from vcf_b200.rd import rd_stats_fused
+    torch = cx.torch
+    H, W = 2160, 3840
+    BS, QS = (4, 8, 16, 32), (4, 8, 12, 16, 24, 32, 48, 64)
+    x = make_frames(torch, frames_per_gpu, H, W, cx.dev, 4321 + cx.rank, "natural")
+    pend = {}
+
+    def step(s, ev=None):
+        if ev:
+            ev[0].record()
+        tab = torch.stack([rd_stats_fused(x, B, QS) for B in BS])       # (4, 8, 776) int64
+        if ev:
+            ev[1].record()
+        if pend.get("work") is not None:
+            pend["work"].wait()
+        pend["v"] = tab
+        pend["work"] = cx.dist.all_reduce(tab, async_op=True) if cx.world > 1 else None
+        if ev:
+            ev[2].record()
+
+    def finalize():
+        if pend.get("work") is not None:
+            pend["work"].wait()
+            pend["work"] = None
+
+    ms, sweep_ms, _, launches, _ = timed_steps(cx, step, a.steps, a.warmup, finalize=finalize)
+    npts = len(BS) * len(QS)
+    px = frames_per_gpu * H * W
+    # one point through the separate kernels, for the ratio (encode + float64 decode + statistics, B = 32, q = 32)
+    from vcf_b200.rd import rd_point
+    rd_point(x, 32, 32)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for B in BS:
+        rd_point(x, B, 32)
+    torch.cuda.synchronize()
+    per_point_ms = (time.perf_counter() - t0) * 1e3 / len(BS)
+    st = pend["v"][1, 5].cpu().numpy()                                   # B = 8, q = 32
+    return {"value": cx.world * px * npts * a.steps / 1e6 / (ms / 1e3), "unit": "Mpixel/s x (B, q) points",
+            "ms_per_step": ms / a.steps, "ms_per_sweep_kernels": sweep_ms, "points": npts,
+            "frames_per_gpu_per_step": frames_per_gpu, "kernel": _lib.last_kernel(), "gpu_launches": launches,
+            "alg_bytes_per_step": 3.0 * px * len(BS), "per_point_path_ms_per_point": per_point_ms,
+            "speedup_over_per_point_path": per_point_ms * npts / (ms / a.steps),
+            "check_B8_q32": {"sse": int(st[0:3].sum()), "nonzero": int(st[4])},
+            "bound": "issue slots / FP64 pipe (float64 inverse chain per step), not HBM: profiles/r2_rd_sweep_ncu_summary.json"}
+
+
 def fracs(cx, px_step, enc_ms, dec_ms, dec_extra_b=0.0):
     p = cx.peak
     return {"encode_frac": 6.0 * px_step / (enc_ms / 1e3) / 1e9 / p,
@@ -665,10 +718,11 @@ def run_ours(a):
             try:
                 total = WORKLOADS[wl][6]
                 n_wl = total // world if wl == "c4" else total
-                r, bufs_, _ = measure_transform(cx, a, wl, n_wl, "natural", wl == "c5")
-                if wl == "c4":
-                    r2, _, _ = measure_transform(cx, a, wl, n_wl, "natural", True, frames=bufs_[0], bufs=bufs_[1:])
-                    r["exact_mode"] = {k: r2[k] for k in ("value", "ms_per_step", "decode_ms_per_launch", "decode_frac", "kernels")}
+                # fast mode first (c4: tensor cores; c5: bit-exact float32 encoder + float32 decoder), the bit-exact pair beside it
+                r, bufs_, _ = measure_transform(cx, a, wl, n_wl, "natural", False)
+                r2, _, _ = measure_transform(cx, a, wl, n_wl, "natural", True, frames=bufs_[0], bufs=bufs_[1:])
+                r["exact_mode"] = {k: r2[k] for k in ("value", "ms_per_step", "encode_ms_per_launch", "decode_ms_per_launch",
+                                                      "encode_frac", "decode_frac", "kernels")}
                 r["config"] = WORKLOADS[wl][7]
                 r["scaling"] = "strong" if wl == "c4" else "weak"
                 workloads[wl] = strip(r)
@@ -676,6 +730,14 @@ def run_ours(a):
             except Exception as exc:
                 workloads[wl] = {"error": repr(exc)}
             torch.cuda.empty_cache()
+        try:
+            r = measure_rd_sweep(cx, a)
+            r["config"] = ("configs[2]: RD sweep on a 3840x2160 frame per GPU, B in {4,8,16,32} x q in {4,8,12,16,24,32,48,64}, "
+                           "fused (forward once per B, every step on chip), statistics all-reduced")
+            r["scaling"] = "weak"
+            workloads["c3"] = r
+        except Exception as exc:
+            workloads["c3"] = {"error": repr(exc)}
     sampler.stop()
 
     if rank != 0:

@@ -397,6 +397,46 @@ def test_fast16_decode_path_exact(q, color, torch_cuda):
     assert np.array_equal(got.cpu().numpy(), O.decode_array(k, img.shape, 16, q, color=color))
 
 
+@pytest.mark.parametrize("color", ["YCoCg", "YCrCb"])
+def test_fast16_float32_decoder_tolerances(color, torch_cuda):
+    """B = 16 fast path, float32 decoder (the fast mode): within +-1 LSB of the reference's float64 chain and
+    PSNR within 0.01 dB, on natural, noise and smooth content; blocks with DC indices only are bit-exact."""
+    from vcf_b200 import _lib
+    t = torch_cuda
+    H, W = 256, 3840
+    for kind, q in (("natural", 8), ("natural", 32), ("noise", 8), ("noise", 32), ("smooth", 32), ("natural", 200)):
+        if kind == "smooth":
+            yy, xx = np.mgrid[0:H, 0:W]
+            img = np.stack([110 + 60 * np.sin(xx / 400.0) * np.cos(yy / 300.0), 90 + 0.02 * xx, 140 - 0.1 * yy], axis=-1)
+            img = np.clip(img, 0, 255).astype(np.uint8)
+        else:
+            img = O.synthetic_frame(H, W, 4000 + q, kind)
+        idx = O.encode_array(img, 16, q, color=color)
+        ref = O.decode_array(idx, img.shape, 16, q, color=color)
+        got = _codec(block_size=16, q=q, color=color).decode(t.from_numpy(idx).cuda(), (H, W)).cpu().numpy()
+        assert _lib.last_kernel() == "dec16_f32"
+        d = np.abs(got.astype(np.int16) - ref.astype(np.int16))
+        assert d.max() <= 1, (kind, q, int(d.max()))
+        assert abs(O.psnr(img, got) - O.psnr(img, ref)) < 0.01, (kind, q, O.psnr(img, got), O.psnr(img, ref))
+        # DC-only blocks: bit-exact
+        k = idx.astype(np.int16) - 128
+        blk = k.reshape(16, H // 16, 16, W // 16, 3)                  # subband layout [j][y][i][x][c]
+        ac = np.abs(blk).sum(axis=(0, 2, 4)) - np.abs(blk[0, :, 0]).sum(axis=-1)
+        dc_only = np.repeat(np.repeat(ac == 0, 16, axis=0), 16, axis=1)
+        assert np.array_equal(got[dc_only], ref[dc_only]), (kind, q)
+        if kind == "smooth":
+            assert dc_only.mean() > 0.05
+    # statistics go with it
+    from vcf_b200.codec import stats_dict
+    img = O.synthetic_frame(64, 512, 4100, "natural")
+    idx = O.encode_array(img, 16, 16, color=color)
+    got, st = _codec(block_size=16, q=16, color=color).decode(t.from_numpy(idx).cuda(), (64, 512),
+                                                              original=t.from_numpy(img).cuda(), stats=True)
+    assert _lib.last_kernel() == "dec16_f32"
+    s = stats_dict(st.cpu().numpy())
+    assert int(s["sse"].sum()) == O.sse_int(img, got.cpu().numpy()) and s["nsamples"] == img.size
+
+
 @pytest.mark.parametrize("q", [1, 8, 12, 32, 64, 255])
 def test_fast_decode_path(q, torch_cuda):
     """TMA decode fast path: float64 mode bit-exact with the reference chain, float32

@@ -75,6 +75,7 @@ int launch_encode_tc(const EncArgs& a, cudaStream_t s);     // fast-mode encoder
 // B = 16 fast path (kernels_b16.cu)
 int launch_encode_fast16(const EncArgs& a, cudaStream_t s);
 int launch_decode_fast16(const DecArgs& a, cudaStream_t s);
+int launch_decode_fast16_f32(const DecArgs& a, cudaStream_t s);   // float32 fast mode (kernels_b16f.cu)
 
 // streaming statistics behind the fast path (kernels_stats.cu); VCFB_E_UNSUPP if unaligned
 int launch_index_stats(const uint8_t* idx, long long n_bytes, bool hist, unsigned long long* stats, cudaStream_t s);
