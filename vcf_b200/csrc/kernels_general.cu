@@ -26,7 +26,12 @@
 namespace vcfb {
 namespace {
 
-constexpr int NT = 256;
+// threads per CTA: B = 32 tiles fill the whole shared memory of an SM (one CTA per SM), so the CTA itself has to
+// bring the warps: 384 threads = one round of the 384 (float64) or two of the 768 (float32) work items of a pass
+#ifndef NT32
+#define NT32 384
+#endif
+template <int B> __host__ __device__ constexpr int nthreads() { return B == 32 ? NT32 : 256; }
 
 __host__ __device__ constexpr int tile_w(int B, int szT) { return (B >= 16 && szT == 8) ? 128 : 256; }
 
@@ -107,7 +112,8 @@ __device__ __forceinline__ unsigned warp_sum(unsigned v) {
 // MODE 0: subband layout, no perceptual weights, no statistics -- every flag a compile-time
 // constant; MODE 1: the same with statistics; MODE 2: everything decided at run time.
 template <typename T, int B, bool EXACT, int MODE>
-__global__ void __launch_bounds__(NT) encode_kernel(const EncArgs a) {
+__global__ void __launch_bounds__(nthreads<B>()) encode_kernel(const EncArgs a) {
+  constexpr int NT = nthreads<B>();
   using L = Layout<T, B>;
   using O = Ops<T, EXACT>;
   using D = Dct<B, false>;
@@ -326,7 +332,8 @@ __global__ void __launch_bounds__(NT) encode_kernel(const EncArgs a) {
 
 // PLAIN: subband layout and no perceptual weights, known at compile time.
 template <typename T, int B, bool EXACT, bool PLAIN>
-__global__ void __launch_bounds__(NT) decode_kernel(const DecArgs a) {
+__global__ void __launch_bounds__(nthreads<B>()) decode_kernel(const DecArgs a) {
+  constexpr int NT = nthreads<B>();
   using L = Layout<T, B>;
   using O = Ops<T, EXACT>;
   using D = Dct<B, true>;
@@ -629,7 +636,7 @@ int launch_enc_mode(const EncArgs& a, cudaStream_t s) {
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(encode)");
   dim3 grid((a.g.Wp + L::TW - 1) / L::TW, a.g.ny, a.n_frames);
   note_kernel("encode_general");
-  kern<<<grid, NT, L::ENC_SMEM, s>>>(a);
+  kern<<<grid, nthreads<B>(), L::ENC_SMEM, s>>>(a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "encode_kernel launch");
   return VCFB_OK;
@@ -650,7 +657,7 @@ int launch_dec_mode(const DecArgs& a, cudaStream_t s) {
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(decode)");
   dim3 grid((a.g.Wp + L::TW - 1) / L::TW, a.g.ny, a.n_frames);
   note_kernel("decode_general");
-  kern<<<grid, NT, L::DEC_SMEM, s>>>(a);
+  kern<<<grid, nthreads<B>(), L::DEC_SMEM, s>>>(a);
   e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "decode_kernel launch");
   return VCFB_OK;
