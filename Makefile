@@ -3,7 +3,7 @@
 NVCC      ?= nvcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
 NVCCFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Iinclude -Ivcf_b200/csrc $(EXTRA)
-SRCS      := vcf_b200/csrc/api.cu vcf_b200/csrc/kernels_general.cu vcf_b200/csrc/kernels_anyb.cu vcf_b200/csrc/kernels_rd.cu vcf_b200/csrc/kernels_fast.cu vcf_b200/csrc/kernels_packed.cu vcf_b200/csrc/kernels_b16.cu vcf_b200/csrc/kernels_b16f.cu vcf_b200/csrc/kernels_dec2t.cu vcf_b200/csrc/kernels_dec32.cu vcf_b200/csrc/kernels_tc.cu vcf_b200/csrc/kernels_color.cu vcf_b200/csrc/kernels_stats.cu vcf_b200/csrc/kernels_motion.cu vcf_b200/csrc/kernels_deflate.cu
+SRCS      := vcf_b200/csrc/api.cu vcf_b200/csrc/kernels_general.cu vcf_b200/csrc/kernels_anyb.cu vcf_b200/csrc/kernels_rd.cu vcf_b200/csrc/kernels_tile.cu vcf_b200/csrc/kernels_fast.cu vcf_b200/csrc/kernels_packed.cu vcf_b200/csrc/kernels_b16.cu vcf_b200/csrc/kernels_b16f.cu vcf_b200/csrc/kernels_dec2t.cu vcf_b200/csrc/kernels_dec32.cu vcf_b200/csrc/kernels_tc.cu vcf_b200/csrc/kernels_color.cu vcf_b200/csrc/kernels_stats.cu vcf_b200/csrc/kernels_motion.cu vcf_b200/csrc/kernels_deflate.cu
 SRCS      := $(wildcard $(SRCS))
 OBJS      := $(patsubst vcf_b200/csrc/%.cu,build/%.o,$(SRCS))
 HDRS      := $(wildcard vcf_b200/csrc/*.cuh) include/vcfb200.h

@@ -397,6 +397,60 @@ def test_fast16_decode_path_exact(q, color, torch_cuda):
     assert np.array_equal(got.cpu().numpy(), O.decode_array(k, img.shape, 16, q, color=color))
 
 
+@pytest.mark.parametrize("B", [32])
+@pytest.mark.parametrize("color", ["YCoCg", "YCrCb"])
+def test_tile_fast_path_b32(B, color, torch_cuda):
+    """B = 32 fast path (csrc/kernels_tile.cu): float32 encoder and float64 decoder bit-exact, float32
+    decoder within +-1 LSB, statistics, vertical padding (2160 rows -> 2176 at B = 32), batches, wrapped indices."""
+    from vcf_b200 import _lib
+    from vcf_b200.codec import stats_dict
+    t = torch_cuda
+    rng = np.random.default_rng(B)
+    for si, (H, W) in enumerate(((64, 256), (40, 384), (100, 128), (96, 1280))):
+        n = 2
+        frames = np.stack([O.synthetic_frame(H, W, 5000 + 10 * si + i, "noise" if i % 2 else "natural") for i in range(n)])
+        x = t.from_numpy(frames).cuda()
+        for q in (1, 8, 12, 32):
+            ref = np.stack([O.encode_array(f, B, q, color=color) for f in frames])
+            got, se = _codec(block_size=B, q=q, color=color, hist=False).encode(x, stats=True)
+            assert _lib.last_kernel() == f"enc{B}_tile", _lib.last_kernel()
+            assert np.array_equal(got.cpu().numpy(), ref), (B, q, H, W, int((got.cpu().numpy() != ref).sum()))
+            got_h, se_h = _codec(block_size=B, q=q, color=color, hist=True).encode(x, stats=True)
+            assert np.array_equal(got_h.cpu().numpy(), ref)
+            idx = ref.copy()
+            if si % 2:
+                idx[-1] = rng.integers(0, 256, size=idx[-1].shape, dtype=np.uint8)
+            refd = np.stack([O.decode_array(k, (H, W, 3), B, q, color=color) for k in idx])
+            dec = _codec(block_size=B, q=q, color=color, fp64=True)
+            gotd, sd = dec.decode(t.from_numpy(idx).cuda(), (H, W), original=x, stats=True)
+            assert _lib.last_kernel() == f"dec{B}_tile", _lib.last_kernel()
+            assert np.array_equal(gotd.cpu().numpy(), refd), (B, q, H, W, int((gotd.cpu().numpy() != refd).sum()))
+            assert np.array_equal(dec.decode(t.from_numpy(idx).cuda(), (H, W)).cpu().numpy(), refd)
+            s = stats_dict((se_h + sd).cpu().numpy())
+            nz, sabs, hist = O.index_stats(ref)
+            assert s["nonzero"] == nz and s["sumabs"] == sabs and np.array_equal(s["hist"], hist) and s["nindices"] == ref.size
+            s0 = stats_dict(se.cpu().numpy())
+            assert s0["nonzero"] == nz and s0["sumabs"] == sabs and s0["nindices"] == ref.size
+            for c in range(3):
+                assert int(s["sse"][c]) == O.sse_int(frames[..., c], refd[..., c])
+            assert s["nsamples"] == frames.size
+            assert s["sumdiff"] == int((frames.astype(np.int64) - refd.astype(np.int64)).sum())
+            got32 = _codec(block_size=B, q=q, color=color).decode(t.from_numpy(ref).cuda(), (H, W)).cpu().numpy()
+            assert _lib.last_kernel() == f"dec{B}_tile_f32"
+            ref32 = np.stack([O.decode_array(k, (H, W, 3), B, q, color=color) for k in ref])
+            assert np.abs(got32.astype(np.int16) - ref32.astype(np.int16)).max() <= 1
+    # numpy entry points (host layer) and a non-integral step
+    img = O.synthetic_frame(64, 256, 5100, "natural")
+    k = _codec(block_size=B, q=2.5, color=color).encode(img)
+    assert np.array_equal(k, O.encode_array(img, B, 2.5, color=color))
+    y = _codec(block_size=B, q=2.5, color=color, fp64=True).decode(k, img.shape)
+    assert np.array_equal(y, O.decode_array(k, img.shape, B, 2.5, color=color))
+    # widths outside the fast path keep the general kernel
+    img = O.synthetic_frame(64, 96, 5101, "natural")
+    _codec(block_size=B, q=8, color=color).encode(t.from_numpy(img).cuda())
+    assert _lib.last_kernel() == "encode_general"
+
+
 @pytest.mark.parametrize("color", ["YCoCg", "YCrCb"])
 def test_fast16_float32_decoder_tolerances(color, torch_cuda):
     """B = 16 fast path, float32 decoder (the fast mode): within +-1 LSB of the reference's float64 chain and

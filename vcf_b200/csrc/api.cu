@@ -125,6 +125,8 @@ int vcfb_encode_dev(const uint8_t* rgb, int n_frames, int H, int W, int B, doubl
   rc = B == 16 ? launch_encode_fast16(a, static_cast<cudaStream_t>(cuda_stream))
                : launch_encode_fast(a, B, static_cast<cudaStream_t>(cuda_stream));
   if (rc != VCFB_E_UNSUPP) return rc;
+  rc = launch_encode_tile(a, B, static_cast<cudaStream_t>(cuda_stream));      // B = 32
+  if (rc != VCFB_E_UNSUPP) return rc;
   return launch_encode_general(a, B, static_cast<cudaStream_t>(cuda_stream));
 }
 
@@ -156,6 +158,8 @@ int vcfb_decode_dev(const uint8_t* idx, int n_frames, int H, int W, int B, doubl
   if (!(flags & VCFB_F_SYNTH_F32)) {      // the upstream-variant decoder exists in the general kernel only
     rc = B == 16 ? launch_decode_fast16(a, static_cast<cudaStream_t>(cuda_stream))
                  : launch_decode_fast(a, B, static_cast<cudaStream_t>(cuda_stream));
+    if (rc != VCFB_E_UNSUPP) return rc;
+    rc = launch_decode_tile(a, B, static_cast<cudaStream_t>(cuda_stream));    // B = 32
     if (rc != VCFB_E_UNSUPP) return rc;
   }
   return launch_decode_general(a, B, static_cast<cudaStream_t>(cuda_stream));

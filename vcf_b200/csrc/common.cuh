@@ -66,6 +66,10 @@ int launch_rd_sweep(const uint8_t* rgb, const Geom& g, int n_frames, int B, cons
 int launch_rd_sweep_anyb(const uint8_t* rgb, const Geom& g, int n_frames, int B, const double* qs, int nq, int color,
                          unsigned flags, unsigned long long* stats, cudaStream_t s);
 
+// fast path for B = 32 (kernels_tile.cu): VCFB_E_UNSUPP means "not covered, use the general kernel"
+int launch_encode_tile(const EncArgs& a, int B, cudaStream_t s);
+int launch_decode_tile(const DecArgs& a, int B, cudaStream_t s);
+
 // fast path (kernels_fast.cu): VCFB_E_UNSUPP means "not covered, use the general kernel"
 int launch_encode_fast(const EncArgs& a, int B, cudaStream_t s);
 int launch_decode_fast(const DecArgs& a, int B, cudaStream_t s);
