@@ -81,6 +81,12 @@ extern "C" {
                                  (src/2D-DCT.py:560-566).  Without it: the indices a decoder reads back from the
                                  code-stream (wrapped to uint8 :361, int16 arithmetic :398-410). */
 
+#define VCFB_F_NO_OFFSET 256u  /* vcfb_encode_dev and vcfb_rd_sweep_dev: neither the -128 on the pixels nor the +128 on the
+                                 indices.  This is what the reference's optimize_block_size actually runs with: it is
+                                 called from __init__ (src/2D-DCT.py:99-103) BEFORE self.offset = 128 is assigned (:107-110),
+                                 while self.offset still is the array [0, 0, 0] left by the colour stage (src/YCoCg.py:28-29) --
+                                 found by running the unmodified reference (tests/golden/ref_flow_L_*.npz). */
+
 #define VCFB_F_HIST 16u       /* statistics: also accumulate the 3 x 256 histogram of the indices
                                  (one shared-memory atomic per sample; off = only the sums) */
 
@@ -156,7 +162,7 @@ int vcfb_decode_dev(const uint8_t* idx, int n_frames, int H, int W, int B, doubl
  * runs per point of src/RDE.py:68-118; the numbers are those vcfb_encode_dev (float32, bit-exact) followed by
  * vcfb_decode_dev (VCFB_F_FP64, bit-exact) with `original` accumulate, step for step.
  * q_steps   n_steps quantisation steps (host array), n_steps <= VCFB_RD_MAX_STEPS
- * flags     VCFB_F_HIST, VCFB_F_NOWRAP; no perceptual weights (the reference's loop applies none)
+ * flags     VCFB_F_HIST, VCFB_F_NOWRAP, VCFB_F_NO_OFFSET; no perceptual weights (the reference's loop applies none)
  * stats     n_steps x VCFB_STAT_LEN int64 on the device, zeroed by the caller: row i is the statistics vector of
  *           q_steps[i] (SSE, NSAMPLES, SUMDIFF of the decoded image; NONZERO, SUMABS, NINDICES, HIST of the indices) */
 #define VCFB_RD_MAX_STEPS 16

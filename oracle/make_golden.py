@@ -45,11 +45,16 @@ CASES = [
     ("b8_q5_noise", 72, 88, "noise", 20, "2D-DCT.py", ["-q", "5"]),
     ("sa_ycocg", 48, 40, "natural", 21, "YCoCg.py", ["-q", "8"]),
     ("sa_ycrcb", 48, 40, "natural", 22, "YCrCb.py", ["-q", "8"]),
+    # -L: the in-process block-size search (src/2D-DCT.py:533-579); the J of every block size is read from the
+    # reference's own debug log (:576).  Bright frames and a small step make the indices leave [-128, 127].
+    ("L_q4_bright", 128, 128, "natural", 31, "2D-DCT.py", ["-L", "50", "-q", "4", "-g"]),
+    ("L_q32", 128, 256, "natural", 32, "2D-DCT.py", ["-L", "2000", "-q", "32", "-g"]),
 ]
 
 
 def run(script, mode, args, env):
-    cmd = [sys.executable, script, mode] + args
+    pre = ["-g"] if "-g" in args else []           # -g / --debug belongs to the top-level parser (src/parser.py:75)
+    cmd = [sys.executable, script] + pre + [mode] + [x for x in args if x != "-g"]
     r = subprocess.run(cmd, cwd=REF_SRC, env=env, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"{cmd} failed:\n{r.stdout}\n{r.stderr}")
@@ -67,6 +72,8 @@ def main():
         tmp = tempfile.mkdtemp(prefix="vcfgold_")
         try:
             img = O.synthetic_frame(H, W, seed, kind)
+            if name == "L_q4_bright":
+                img = np.clip(img.astype(np.int16) + 70, 0, 255).astype(np.uint8)
             src = os.path.join(tmp, "original.png")
             enc = os.path.join(tmp, "encoded")
             dec = os.path.join(tmp, "decoded.png")
@@ -79,8 +86,12 @@ def main():
                 if os.path.exists(f):
                     os.remove(f)
             shutil.copy(src, "/tmp/original.png")
-            run(script, "encode", flags + io_flags, env)
-            run(script, "decode", flags + io_flags, env)
+            log = run(script, "encode", flags + io_flags, env)
+            dflags = [f for i, f in enumerate(flags) if f not in ("-L", "-g") and (i == 0 or flags[i - 1] != "-L")]
+            if "-L" in flags:        # the decoder does not know which block size the encoder chose (:64-66): tell it
+                chosen = int(log.split("optimal block_size=")[1].split()[0])
+                dflags = dflags + ["-B", str(chosen)]
+            run(script, "decode", dflags + io_flags, env)
             shutil.copy("/tmp/encoded.npz", enc + ".npz")
             shutil.copy("/tmp/decoded.png", dec)
             if script == "2D-DCT.py":
@@ -90,6 +101,16 @@ def main():
             idx = np.load(enc + ".npz")["a"]
             out = cv2.cvtColor(cv2.imread(dec, cv2.IMREAD_UNCHANGED), cv2.COLOR_BGR2RGB)
             extra = {}
+            if "-L" in flags:
+                Bs, Js = [], []
+                for line in log.splitlines():
+                    if "J=" in line and "block_size=" in line:
+                        Js.append(float(line.split("J=")[1].split()[0]))
+                        Bs.append(int(line.split("block_size=")[1].split()[0]))
+                extra["L_block_sizes"] = np.array(Bs, dtype=np.int64)
+                extra["L_J"] = np.array(Js, dtype=np.float64)
+                extra["L_chosen"] = np.int64(chosen)
+                extra["L_lambda"] = np.float64(flags[flags.index("-L") + 1])
             if name == "default_96x80":
                 txt = subprocess.run(
                     [sys.executable, "RDE.py", "-o", src, "-c", enc + ".npz", "-d", dec],

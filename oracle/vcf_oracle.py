@@ -436,27 +436,34 @@ def rmse(a: np.ndarray, b: np.ndarray):
     return np.sqrt((d ** 2).mean())
 
 
-def optimize_block_size_point(img_u8: np.ndarray, B: int, q, *, color: str = "YCoCg"):
+def optimize_block_size_point(img_u8: np.ndarray, B: int, q, *, color: str = "YCoCg", offset=0):
     """One iteration of the loop of src/2D-DCT.py:538-578 (optimize_block_size), returning
-    ``(k_u8, y_u8, RMSE)``: the array handed to ``self.compress`` (:559), the reconstruction (:571) and
-    the distortion the reference forms (:574) -- between the image STILL SHIFTED by 128 (:536-537) and
-    the un-shifted reconstruction.  Differences from encode_fn + decode_fn that a drop-in must keep: no
-    padding (:536; shapes must be multiples of B), no perceptual scaling, and the dequantiser receives the
-    quantiser's own integer indices (:565-566) -- never narrowed to uint8, never int16."""
+    ``(k_u8, y_u8, RMSE)``: the array handed to ``self.compress`` (:559), the reconstruction (:573) and
+    the distortion the reference forms (:574).  Differences from encode_fn + decode_fn that a drop-in must keep:
+
+    * ``offset`` is 0, not 128: the loop is called from ``__init__`` (:99-103) BEFORE ``self.offset = 128`` is
+      assigned (:107-110); ``self.offset`` still holds the ``np.array([0, 0, 0])`` that the colour stage's
+      ``__init__`` left there (src/YCoCg.py:28-29).  So the image is not centred, the indices are not biased and
+      the reconstruction is not shifted back (:537, :557, :566, :572 all add or subtract zeros).  Pinned by
+      running the unmodified reference: tests/golden/ref_flow_L_*.npz (oracle/make_golden.py records the J the
+      reference logs per block size).  ``offset=128`` evaluates the loop as its author presumably intended;
+    * no padding (:536; shapes must be multiples of B) and no perceptual scaling;
+    * the dequantiser receives the quantiser's own integer indices (:565-568) -- never narrowed to uint8 (only
+      the argument of ``compress`` is, :559, wrapping modulo 256), never int16."""
     img = img_u8.astype(np.float32)                              # :536
-    img -= OFFSET                                                # :537
+    img -= offset                                                # :537
     ct = ycocg_from_rgb(img) if color == "YCoCg" else ycrcb_from_rgb_float(img)   # :540
     coef = analyze_image(ct, B, B)                               # :541
     decom = get_subbands(coef, B, B)                             # :542
     Q = DeadzoneQuantizer(q)
     k = Q.encode(decom)                                          # :556
-    k += OFFSET                                                  # :557
-    k_u8 = k.astype(np.uint8)                                    # :563 (argument of compress)
-    k -= OFFSET                                                  # :566
+    k += offset                                                  # :557
+    k_u8 = k.astype(np.uint8)                                    # :559 (argument of compress)
+    k -= offset                                                  # :566
     y = Q.decode(k)                                              # :568 (int64 * q)
     ct_y = synthesize_image(get_blocks(y, B, B), B, B)           # :569-570 (float64)
     y = ycocg_to_rgb(ct_y) if color == "YCoCg" else ycrcb_to_rgb_float(ct_y)      # :571
-    y += OFFSET                                                  # :572
+    y += offset                                                  # :572
     y = np.clip(y, 0, 255).astype(np.uint8)                      # :573
     return k_u8, y, rmse(img, y)                                 # :574
 

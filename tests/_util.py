@@ -17,6 +17,18 @@ def parse_flags(flags):
             kw["disable_subbands"] = True; i += 1
         elif f == "-t":
             i += 2   # the reference keeps the YCoCg arithmetic (src/2D-DCT.py:22-23)
+        elif f == "-L":
+            i += 2   # block-size search: the chosen size is recorded with the vector (L_chosen)
+        elif f == "-g":
+            i += 1
         else:
             raise AssertionError(f)
+    return kw
+
+
+def golden_kw(g):
+    """Codec keywords of a golden vector; a -L vector was encoded with the block size the search chose."""
+    kw = parse_flags(g["flags"])
+    if "L_chosen" in g.files:
+        kw["B"] = int(g["L_chosen"])
     return kw

@@ -9,7 +9,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 from oracle import vcf_oracle as O
-from _util import parse_flags as _parse
+from _util import golden_kw as _gkw, parse_flags as _parse
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -35,7 +35,7 @@ FILES = sorted(f for f in glob.glob(os.path.join(GOLD, "ref_flow_*.npz")) if "sa
 @pytest.mark.parametrize("fn", FILES, ids=[os.path.basename(f)[9:-4] for f in FILES])
 def test_reference_golden_bit_exact(fn, torch_cuda):
     g = np.load(fn)
-    kw = _parse(g["flags"])
+    kw = _gkw(g)
     c32 = _codec(block_size=kw["B"], q=kw["q"], perceptual=kw["perceptual"],
                  disable_subbands=kw["disable_subbands"])
     idx = c32.encode(g["img"])

@@ -61,22 +61,34 @@ def test_nowrap_is_the_references_in_process_loop(B, t):
     img = np.clip(O.synthetic_frame(128, 256, 800 + B, "natural").astype(np.int16) + 90, 0, 255).astype(np.uint8)
     img[:64] = np.clip(img[:64].astype(np.int16) - 200, 0, 255).astype(np.uint8)
     qs = (1, 3, 8, 32)
-    got = rd_stats_fused(t.from_numpy(img).cuda(), B, qs, nowrap=True).cpu().numpy()
     wrapped_differs = False
-    for i, q in enumerate(qs):
-        k_u8, y, rm = O.optimize_block_size_point(img, B, q)
-        st = stats_dict(got[i])
-        d = img.astype(np.int64) - y.astype(np.int64)
-        assert int(st["sse"].sum()) == int((d * d).sum()), (B, q)
-        assert st["sumdiff"] == int(d.sum()) and st["nsamples"] == img.size
-        nz, sabs, hist = O.index_stats(k_u8)
-        assert st["nonzero"] == nz and st["sumabs"] == sabs and np.array_equal(st["hist"], hist)
-        # the distortion the reference forms (:574): image still shifted by 128
-        n = st["nsamples"]
-        se = float(st["sse"].sum()) - 256.0 * st["sumdiff"] + 16384.0 * n
-        assert abs(np.sqrt(se / n) - float(rm)) <= 2e-6 * float(rm) + 1e-6
-        y_wrapped = O.decode_array(k_u8, img.shape, B, q)
-        wrapped_differs |= not np.array_equal(y_wrapped, y)
+    for offset in (0, 128):        # 0 = the loop as the reference runs it (VCFB_F_NO_OFFSET), 128 = as it reads
+        got = rd_stats_fused(t.from_numpy(img).cuda(), B, qs, nowrap=True, no_offset=offset == 0).cpu().numpy()
+        for i, q in enumerate(qs):
+            k_u8, y, rm = O.optimize_block_size_point(img, B, q, offset=offset)
+            st = stats_dict(got[i])
+            d = img.astype(np.int64) - y.astype(np.int64)
+            assert int(st["sse"].sum()) == int((d * d).sum()), (B, q, offset)
+            assert st["sumdiff"] == int(d.sum()) and st["nsamples"] == img.size
+            hist = np.stack([np.bincount(k_u8[..., c].ravel(), minlength=256) for c in range(3)])
+            assert np.array_equal(st["hist"], hist), (B, q, offset)
+            n = st["nsamples"]
+            if offset:      # the distortion as the loop reads (:574): image still shifted by 128
+                se = float(st["sse"].sum()) - 256.0 * st["sumdiff"] + 16384.0 * n
+                nz, sabs, _ = O.index_stats(k_u8)
+                assert st["nonzero"] == nz and st["sumabs"] == sabs
+            else:           # as it runs: plain RMSE
+                se = float(st["sse"].sum())
+                k8 = k_u8.astype(np.int8).astype(np.int64)
+                assert st["nonzero"] == int((k8 != 0).sum()) and st["sumabs"] == int(np.abs(k8).sum())
+            assert abs(np.sqrt(se / n) - float(rm)) <= 2e-6 * float(rm) + 1e-6
+            if offset:
+                y_wrapped = O.decode_array(k_u8, img.shape, B, q)
+                wrapped_differs |= not np.array_equal(y_wrapped, y)
+            # the array handed to the entropy coder: the encoder with the same flag
+            from vcf_b200 import Codec
+            k_gpu = Codec(block_size=B, q=q, no_offset=offset == 0).encode(t.from_numpy(img).cuda()).cpu().numpy()
+            assert np.array_equal(k_gpu, k_u8), (B, q, offset)
     assert wrapped_differs                  # the test does exercise the difference
 
 

@@ -89,11 +89,11 @@ def test_iii_style_per_frame_loop_and_block_size_optimiser():
     # -L: J = rate + Lambda*RMSE over 2**i, i = 1..7 (src/2D-DCT.py:533-579; 128 does not divide the frame)
     img = frames[0]
     _write_png("/tmp/original.png", img)
-    r = _run(STUB, PLUGIN, "encode", "-L", "50.0", "-q", "16", "-g")
+    r = _run(STUB, PLUGIN, "-g", "encode", "-L", "50.0", "-q", "16")
     assert r.returncode == 0, r.stderr[-2000:]
     best, bestJ = None, 1e18
     for B in (2, 4, 8, 16, 32, 64):
-        k, y, rm = O.optimize_block_size_point(img, B, 16)     # the reference's loop body, :538-574
+        k, y, rm = O.optimize_block_size_point(img, B, 16)     # the reference's loop body as it runs, :538-574
         b = io.BytesIO()
         np.savez_compressed(file=b, a=k)
         J = len(b.getvalue()) + 50.0 * rm
@@ -101,6 +101,27 @@ def test_iii_style_per_frame_loop_and_block_size_optimiser():
             best, bestJ = B, J
     assert f"optimal block_size={best}" in r.stderr, r.stderr[-1500:]
     assert np.array_equal(np.load("/tmp/encoded.npz")["a"], O.encode_array(img, best, 16))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["L_q4_bright", "L_q32"])
+def test_block_size_search_reproduces_the_references_log(name):
+    """The J the plugin logs per block size against the J the UNMODIFIED reference logged for the same image and
+    flags (tests/golden/ref_flow_L_*.npz, oracle/make_golden.py), the chosen size and the code-stream."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"ref_flow_{name}.npz"))
+    _write_png("/tmp/original.png", g["img"])
+    flags = [str(f) for f in g["flags"] if str(f) != "-g"]
+    r = _run(STUB, PLUGIN, "-g", "encode", *flags)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = {}
+    for line in r.stderr.splitlines():
+        if "J=" in line and "block_size=" in line:
+            got[int(line.split("block_size=")[1].split()[0])] = float(line.split("J=")[1].split()[0])
+    assert sorted(got) == [int(b) for b in g["L_block_sizes"]]
+    for B, J_ref in zip(g["L_block_sizes"], g["L_J"]):
+        assert abs(got[int(B)] - float(J_ref)) <= 2e-6 * float(J_ref), (int(B), got[int(B)], float(J_ref))
+    assert f"optimal block_size={int(g['L_chosen'])}" in r.stderr
+    assert np.array_equal(np.load("/tmp/encoded.npz")["a"], g["idx"])
 
 
 def test_plugin_registers_reference_flags_without_gpu():

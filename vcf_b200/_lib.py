@@ -17,7 +17,7 @@ STAT_NONZERO, STAT_SUMABS, STAT_NINDICES, STAT_SUMDIFF, STAT_HIST = 4, 5, 6, 7, 
 STAT_LEN = 8 + 3 * 256
 
 COLOR_YCOCG, COLOR_YCRCB = 0, 1
-F_NO_SUBBANDS, F_PERCEPTUAL, F_FP64, F_CONTRACT, F_HIST, F_SYNTH_F32, F_FAST, F_NOWRAP = 1, 2, 4, 8, 16, 32, 64, 128
+F_NO_SUBBANDS, F_PERCEPTUAL, F_FP64, F_CONTRACT, F_HIST, F_SYNTH_F32, F_FAST, F_NOWRAP, F_NO_OFFSET = 1, 2, 4, 8, 16, 32, 64, 128, 256
 RD_MAX_STEPS = 16
 
 

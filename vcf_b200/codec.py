@@ -22,7 +22,7 @@ from typing import Optional
 import numpy as np
 
 from . import _lib
-from ._lib import (COLOR_YCOCG, COLOR_YCRCB, F_CONTRACT, F_FP64, F_HIST, F_NO_SUBBANDS, F_PERCEPTUAL, F_FAST, F_SYNTH_F32,
+from ._lib import (COLOR_YCOCG, COLOR_YCRCB, F_CONTRACT, F_FP64, F_HIST, F_NO_SUBBANDS, F_PERCEPTUAL, F_FAST, F_SYNTH_F32, F_NO_OFFSET,
                    STAT_HIST, STAT_LEN, VcfbError, check, padded_dims)
 
 _COLORS = {"YCoCg": COLOR_YCOCG, "YCrCb": COLOR_YCRCB}
@@ -84,7 +84,8 @@ class Codec:
 
     def __init__(self, block_size: int = 8, q=32, color: str = "YCoCg", perceptual: bool = False,
                  disable_subbands: bool = False, fp64: bool = False, contract: bool = False,
-                 device: Optional[int] = None, hist: bool = True, synth_f32: bool = False, fast: bool = False):
+                 device: Optional[int] = None, hist: bool = True, synth_f32: bool = False, fast: bool = False,
+                 no_offset: bool = False):
         if color not in _COLORS:
             raise ValueError(f"color must be one of {list(_COLORS)}")
         if block_size not in (2, 4, 8, 16, 32, 64, 128):      # the reference's -L search set (src/2D-DCT.py:538)
@@ -97,7 +98,8 @@ class Codec:
         self.flags = ((F_PERCEPTUAL if perceptual else 0) | (F_NO_SUBBANDS if disable_subbands else 0)
                       | (F_FP64 if fp64 else 0) | (F_CONTRACT if contract else 0)
                       | (F_HIST if hist else 0)       # histogram of the indices in the statistics
-                      | (F_FAST if fast else 0))      # encode: tensor-core fast mode (< 1e-6 of the indices differ)
+                      | (F_FAST if fast else 0)       # encode: tensor-core fast mode (< 1e-6 of the indices differ)
+                      | (F_NO_OFFSET if no_offset else 0))   # encode only: the offset-free loop of optimize_block_size
         # decode only: upstream variant "synthesize_image stores float32" (include/vcfb200.h)
         self.synth_f32 = bool(synth_f32)
         if synth_f32 and not fp64:
@@ -109,7 +111,7 @@ class Codec:
         self._ctx = None
 
     def _dec_flags(self):
-        return self.flags | (F_SYNTH_F32 if self.synth_f32 else 0)
+        return (self.flags & ~F_NO_OFFSET) | (F_SYNTH_F32 if self.synth_f32 else 0)
 
     # -- plumbing ---------------------------------------------------------------
     def __del__(self):

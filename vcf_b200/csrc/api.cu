@@ -51,7 +51,7 @@ static int check_common(const void* in, int n_frames, int H, int W, int B, doubl
   if ((flags & VCFB_F_PERCEPTUAL) && !weights) { set_error("VCFB_F_PERCEPTUAL needs weights"); return VCFB_E_ARG; }
   if ((flags & VCFB_F_FP64) && (flags & VCFB_F_CONTRACT)) { set_error("VCFB_F_CONTRACT is float32 only"); return VCFB_E_ARG; }
   if ((flags & VCFB_F_SYNTH_F32) && !(flags & VCFB_F_FP64)) { set_error("VCFB_F_SYNTH_F32 is a variant of the float64 decoder: set VCFB_F_FP64 too"); return VCFB_E_ARG; }
-  if (flags & ~(VCFB_F_NO_SUBBANDS | VCFB_F_PERCEPTUAL | VCFB_F_FP64 | VCFB_F_CONTRACT | VCFB_F_HIST | VCFB_F_SYNTH_F32 | VCFB_F_FAST)) { set_error("unknown flag bits"); return VCFB_E_ARG; }
+  if (flags & ~(VCFB_F_NO_SUBBANDS | VCFB_F_PERCEPTUAL | VCFB_F_FP64 | VCFB_F_CONTRACT | VCFB_F_HIST | VCFB_F_SYNTH_F32 | VCFB_F_FAST | VCFB_F_NO_OFFSET)) { set_error("unknown flag bits"); return VCFB_E_ARG; }
   return VCFB_OK;
 }
 
@@ -111,6 +111,7 @@ int vcfb_encode_dev(const uint8_t* rgb, int n_frames, int H, int W, int B, doubl
   a.weights = weights;
   a.stats = reinterpret_cast<unsigned long long*>(stats);
   if (anyb_supported(B)) return launch_encode_anyb(a, B, static_cast<cudaStream_t>(cuda_stream));
+  if (flags & VCFB_F_NO_OFFSET) return launch_encode_general(a, B, static_cast<cudaStream_t>(cuda_stream));
   if ((flags & VCFB_F_FAST) && B == 8 && !(flags & VCFB_F_FP64)) {
     // fast mode: tensor-core encoder; statistics, when asked for, by the streaming pass over the indices
     static const bool tc_off = getenv("VCFB_TC") && getenv("VCFB_TC")[0] == '0';
@@ -138,6 +139,7 @@ int vcfb_decode_dev(const uint8_t* idx, int n_frames, int H, int W, int B, doubl
   int rc = check_common(idx, n_frames, H, W, B, q, color, flags, weights, &a.g);
   if (rc) return rc;
   if (!rgb_out && !y_out && !(original && stats)) { set_error("decode has no output"); return VCFB_E_ARG; }
+  if (flags & VCFB_F_NO_OFFSET) { set_error("VCFB_F_NO_OFFSET is an encode / rd_sweep flag (the reference's decoder always runs with offset 128)"); return VCFB_E_ARG; }
   if (q == floor(q) && q >= 32768.0) {
     // numpy refuses `python int * int16 array` when the int does not fit int16 (src/2D-DCT.py:410)
     set_error("integral quantisation step does not fit int16: the reference's dequantiser raises OverflowError");
@@ -170,7 +172,7 @@ int vcfb_rd_sweep_dev(const uint8_t* rgb, int n_frames, int H, int W, int B, con
   Geom g;
   if (!q_steps || n_steps < 1 || n_steps > VCFB_RD_MAX_STEPS) { set_error("n_steps must be in [1, VCFB_RD_MAX_STEPS]"); return VCFB_E_ARG; }
   if (!stats) { set_error("stats is NULL"); return VCFB_E_ARG; }
-  if (flags & ~(VCFB_F_HIST | VCFB_F_NOWRAP)) { set_error("vcfb_rd_sweep_dev takes VCFB_F_HIST and VCFB_F_NOWRAP only"); return VCFB_E_ARG; }
+  if (flags & ~(VCFB_F_HIST | VCFB_F_NOWRAP | VCFB_F_NO_OFFSET)) { set_error("vcfb_rd_sweep_dev takes VCFB_F_HIST, VCFB_F_NOWRAP and VCFB_F_NO_OFFSET only"); return VCFB_E_ARG; }
   for (int i = 0; i < n_steps; ++i) {
     int rc = check_common(rgb, n_frames, H, W, B, q_steps[i], color, 0, nullptr, &g);
     if (rc) return rc;
@@ -481,6 +483,7 @@ int vcfb_decode_host(vcfb_ctx* c, const uint8_t* idx, int n_frames, int H, int W
   int rc = check_common(idx, n_frames, H, W, B, q, color, flags, weights, &g);
   if (rc) return rc;
   if (!rgb_out && !y_out && !(original && stats)) { set_error("decode has no output"); return VCFB_E_ARG; }
+  if (flags & VCFB_F_NO_OFFSET) { set_error("VCFB_F_NO_OFFSET is an encode / rd_sweep flag (the reference's decoder always runs with offset 128)"); return VCFB_E_ARG; }
   HostScope scope(c);
   cudaError_t e = scope.err;
   if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");

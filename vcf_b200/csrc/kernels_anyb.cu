@@ -65,13 +65,13 @@ __device__ __forceinline__ T dag_out(const DagProgram& p, const T* s, int k) {
 
 // forward colour transform of the centred pixel, channel c (kernels_general.cu::color_fwd, not lazy)
 template <typename T, bool EXACT>
-__device__ __forceinline__ T color_fwd(int color, int c, int R, int G, int Bc) {
+__device__ __forceinline__ T color_fwd(int color, int c, int R, int G, int Bc, int poff) {
   using O = Ops<T, EXACT>;
   if (color == VCFB_COLOR_YCOCG) {   // exact for 8-bit input in any evaluation order (src/2D-DCT.py:292-298)
-    const int v = (c == 0) ? (R + 2 * G + Bc - 512) : (c == 1) ? (R - Bc) : (2 * G - R - Bc);
+    const int v = (c == 0) ? (R + 2 * G + Bc - 4 * poff) : (c == 1) ? (R - Bc) : (2 * G - R - Bc);
     return T(v) * T(c == 1 ? 0.5 : 0.25);
   }
-  const T r = T(R - 128), g = T(G - 128), b = T(Bc - 128);
+  const T r = T(R - poff), g = T(G - poff), b = T(Bc - poff);
   const T y = O::add(O::add(O::mul(r, T(0.299)), O::mul(g, T(0.587))), O::mul(b, T(0.114)));
   if (c == 0) return y;
   if (c == 1) return O::mul(O::sub(r, y), T(0.713));
@@ -95,14 +95,15 @@ __global__ void __launch_bounds__(NT) anyb_enc_cols(const EncArgs a, int B, int 
   const DagProgram p = dag_program(B, false);
   T s[DAGP_MAX_SLOTS];
   const int gx = x - g.left;
+  const int poff = (a.flags & VCFB_F_NO_OFFSET) ? 0 : 128;
   for (int r = 0; r < B; ++r) {
     const int gy = by * B + r - g.top;
     T v;
     if (gy >= 0 && gy < g.H && gx >= 0 && gx < g.W) {
       const uint8_t* px = a.rgb + ((size_t(f) * g.H + gy) * g.W + gx) * 3;
-      v = color_fwd<T, EXACT>(a.color, c, px[0], px[1], px[2]);
+      v = color_fwd<T, EXACT>(a.color, c, px[0], px[1], px[2], poff);
     } else {
-      v = color_fwd<T, EXACT>(a.color, c, 0, 0, 0);   // zero padding BEFORE the -128 (:216-227, :292)
+      v = color_fwd<T, EXACT>(a.color, c, 0, 0, 0, poff);   // zero padding BEFORE the -128 (:216-227, :292)
     }
     s[r] = v;
   }
@@ -144,7 +145,8 @@ __global__ void __launch_bounds__(NT) anyb_enc_rows(const EncArgs a, int B, int 
       if (percep) coef = T(double(coef) * wt[i]);                 // src/2D-DCT.py:322-324
       const T tq = a.q_pow2 ? O::mul(coef, inv_q) : O::div(coef, q);   // src/deadzone.py:98
       const int k = to_int_rz<T>(tq);
-      const unsigned byte = unsigned(k + 128) & 255u;             // src/2D-DCT.py:348,:361 (wraps)
+      const int poff = (a.flags & VCFB_F_NO_OFFSET) ? 0 : 128;
+      const unsigned byte = unsigned(k + poff) & 255u;            // src/2D-DCT.py:348,:361 (wraps)
       size_t row, col;
       if (nosub) {
         row = y;
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(NT) anyb_enc_rows(const EncArgs a, int B, int 
       }
       a.idx[((size_t(f) * g.Hp + row) * g.Wp + col) * 3 + c] = uint8_t(byte);
       if (do_stats) {
-        const int kk = int(byte) - 128;
+        const int kk = poff ? int(byte) - 128 : int((signed char)byte);
         nz += (kk != 0);
         sabs += unsigned(kk < 0 ? -kk : kk);
         if (do_hist) atomicAdd(a.stats + VCFB_STAT_HIST + c * 256 + byte, 1ULL);
@@ -188,8 +190,9 @@ __global__ void __launch_bounds__(NT) anyb_rd_quant(const float* coef, double* d
     const float v = coef[item];
     const float tq = q_pow2 ? OF::mul(v, float(1.0 / qd)) : OF::div(v, float(qd));
     const int k = __float2int_rz(tq);
-    const unsigned byte = unsigned(k + 128) & 255u;
-    const int k8 = int(byte) - 128;
+    const int poff = (flags & VCFB_F_NO_OFFSET) ? 0 : 128;
+    const unsigned byte = unsigned(k + poff) & 255u;
+    const int k8 = poff ? int(byte) - 128 : int((signed char)byte);
     nz = (k8 != 0);
     sabs = unsigned(k8 < 0 ? -k8 : k8);
     if (flags & VCFB_F_HIST) atomicAdd(stats + VCFB_STAT_HIST + c * 256 + byte, 1ULL);
@@ -310,9 +313,10 @@ __global__ void __launch_bounds__(NT) anyb_dec_pixels(const DecArgs a, int f, vo
         G = O::add(O::add(c0, O::mul(c1, T(-0.714))), O::mul(c2, T(-0.344)));
         Bv = O::add(c0, O::mul(c2, T(1.773)));
       }
-      R = O::add(R, T(128));               // :454
-      G = O::add(G, T(128));
-      Bv = O::add(Bv, T(128));
+      const T yoff = T((a.flags & VCFB_F_NO_OFFSET) ? 0 : 128);
+      R = O::add(R, yoff);                 // :454 (:572 in the loop of optimize_block_size)
+      G = O::add(G, yoff);
+      Bv = O::add(Bv, yoff);
     }
     const size_t po = ((size_t(f) * g.H + gy) * g.W + gx) * 3;
     if (a.y_out) {
@@ -406,7 +410,7 @@ int launch_rd_sweep_anyb(const uint8_t* rgb, const Geom& g, int n_frames, int B,
   ea.rgb = rgb; ea.g = g; ea.n_frames = n_frames; ea.color = color; ea.flags = flags & ~VCFB_F_NOWRAP;
   DecArgs da;
   memset(&da, 0, sizeof(da));
-  da.g = g; da.n_frames = n_frames; da.color = color; da.flags = VCFB_F_FP64; da.original = rgb;
+  da.g = g; da.n_frames = n_frames; da.color = color; da.flags = VCFB_F_FP64 | (flags & VCFB_F_NO_OFFSET); da.original = rgb;
   for (int f = 0; f < n_frames; ++f) {
     note_kernel("rd_sweep_anyb");
     anyb_enc_cols<float, true><<<blocks_for(3LL * g.ny * g.Wp), NT, 0, s>>>(ea, B, f, fplane);

@@ -84,13 +84,13 @@ template <> __device__ __forceinline__ int to_int_rz<double>(double x) { return 
 // order for 8-bit input, src/2D-DCT.py:292-298.  YCrCb is the float extension
 // of oracle/vcf_oracle.py::ycrcb_from_rgb_float, operation for operation.
 template <typename T, bool EXACT>
-__device__ __forceinline__ T color_fwd(int color, int c, int R, int G, int Bc) {
+__device__ __forceinline__ T color_fwd(int color, int c, int R, int G, int Bc, int poff = 128) {   // poff: src/2D-DCT.py:292
   using O = Ops<T, EXACT>;
   if (color == VCFB_COLOR_YCOCG) {
-    int v = (c == 0) ? (R + 2 * G + Bc - 512) : (c == 1) ? (R - Bc) : (2 * G - R - Bc);
+    int v = (c == 0) ? (R + 2 * G + Bc - 4 * poff) : (c == 1) ? (R - Bc) : (2 * G - R - Bc);
     return T(v);
   }
-  const T r = T(R - 128), g = T(G - 128), b = T(Bc - 128);
+  const T r = T(R - poff), g = T(G - poff), b = T(Bc - poff);
   const T y = O::add(O::add(O::mul(r, T(0.299)), O::mul(g, T(0.587))), O::mul(b, T(0.114)));
   if (c == 0) return y;
   if (c == 1) return O::mul(O::sub(r, y), T(0.713));
@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(nthreads<B>()) encode_kernel(const EncArgs a) 
   const bool percep = MODE == 2 && (a.flags & VCFB_F_PERCEPTUAL) != 0;
   const bool do_stats = MODE != 0 && a.stats != nullptr;
   const bool do_hist = do_stats && (a.flags & VCFB_F_HIST) != 0;
+  const int poff = (MODE == 2 && (a.flags & VCFB_F_NO_OFFSET)) ? 0 : 128;   // the loop of optimize_block_size runs without offset
   const int nruns = nosub ? B : B * B;
   const int runlen = nosub ? nbx * B * 3 : nbx * 3;
   const int rpitch = nosub ? L::RP_NOSUB : L::RP_SUB;
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(nthreads<B>()) encode_kernel(const EncArgs a) 
         const uint8_t* px = raw + r * RAWP + x * 3;
         const int R = px[0], G = px[1], Bc = px[2];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) v[c][r] = color_fwd<T, EXACT>(a.color, c, R, G, Bc);
+        for (int c = 0; c < 3; ++c) v[c][r] = color_fwd<T, EXACT>(a.color, c, R, G, Bc, poff);
       }
       const int xs = L::swz(x);
 #pragma unroll
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(nthreads<B>()) encode_kernel(const EncArgs a) 
 #pragma unroll
       for (int r = 0; r < B; ++r) {
         const uint8_t* px = raw + r * RAWP + x * 3;
-        v[r] = color_fwd<T, EXACT>(a.color, c, px[0], px[1], px[2]);
+        v[r] = color_fwd<T, EXACT>(a.color, c, px[0], px[1], px[2], poff);
       }
       D::template run<T, EXACT>(v);
       const int xs = L::swz(x);
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(nthreads<B>()) encode_kernel(const EncArgs a) 
             tq = a.q_pow2 ? O::mul(coef, inv_q) : O::div(coef, q);  // src/deadzone.py:98
           }
           const int k = to_int_rz<T>(tq);                // truncation = dead zone
-          const unsigned byte = unsigned(k + 128) & 255u;  // src/2D-DCT.py:348,:361 (wraps)
+          const unsigned byte = unsigned(k + poff) & 255u;  // src/2D-DCT.py:348,:361 (wraps)
           int run, off;
           if (nosub) {
             run = u;
@@ -277,7 +278,7 @@ __global__ void __launch_bounds__(nthreads<B>()) encode_kernel(const EncArgs a) 
           }
           stage[run * rpitch + rshift[run] + off] = uint8_t(byte);
           if (do_stats) {
-            const int kk = int(byte) - 128;
+            const int kk = poff ? int(byte) - 128 : int((signed char)byte);
             nz += (kk != 0);
             sabs += unsigned(kk < 0 ? -kk : kk);
             if (do_hist) atomicAdd(&shist[c * 256 + byte], 1u);
@@ -644,7 +645,7 @@ int launch_enc_mode(const EncArgs& a, cudaStream_t s) {
 
 template <typename T, int B, bool EXACT>
 int launch_enc(const EncArgs& a, cudaStream_t s) {
-  const bool plain = !(a.flags & (VCFB_F_NO_SUBBANDS | VCFB_F_PERCEPTUAL));
+  const bool plain = !(a.flags & (VCFB_F_NO_SUBBANDS | VCFB_F_PERCEPTUAL | VCFB_F_NO_OFFSET));
   if (EXACT && plain) return a.stats ? launch_enc_mode<T, B, EXACT, 1>(a, s) : launch_enc_mode<T, B, EXACT, 0>(a, s);
   return launch_enc_mode<T, B, EXACT, 2>(a, s);
 }

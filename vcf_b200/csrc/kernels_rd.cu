@@ -72,18 +72,18 @@ __device__ __forceinline__ unsigned warp_sum(unsigned v) { return __reduce_add_s
 // Phase A of one step for one row of B coefficients, with everything that depends only on the step a
 // compile-time constant (the uniform branches otherwise sit inside the unrolled element loop).
 template <int B, bool POW2, bool QINT, bool NOWRAP>
-__device__ __forceinline__ void quantise_row(const float (&coef)[B], float q, float inv_q, int q_int, double qd,
+__device__ __forceinline__ void quantise_row(const float (&coef)[B], float q, float inv_q, int q_int, double qd, int poff,
                                              double* dst, unsigned* hist_c, bool do_hist, unsigned& nz, unsigned& sabs) {
   using OF = Ops<float, true>;
 #pragma unroll
   for (int i = 0; i < B; ++i) {
     const float tq = POW2 ? OF::mul(coef[i], inv_q) : OF::div(coef[i], q);   // src/deadzone.py:98
     const int k = __float2int_rz(tq);                       // truncation = dead zone
-    const unsigned byte = unsigned(k + 128) & 255u;         // src/2D-DCT.py:348,:361 (wraps)
-    const int k8 = int(byte) - 128;                         // what a decoder reads back (:398,:402)
+    const unsigned byte = unsigned(k + poff) & 255u;        // src/2D-DCT.py:348,:361 (wraps)
+    const int k8 = int((signed char)(byte ^ unsigned(poff)));   // what a decoder reads back (:398,:402): byte - 128 (or int8 without offset)
     nz += (k8 != 0);
     sabs += unsigned(abs(k8));
-    if (do_hist && k8 != 0) atomicAdd(&hist_c[byte], 1u);   // bin 128 is counted through nz
+    if (do_hist && k8 != 0) atomicAdd(&hist_c[byte], 1u);   // the bin of the zero index is counted through nz
     double y;
     if (NOWRAP) y = QINT ? double((long long)k * q_int) : double(k) * qd;          // :565-568 (int64 indices)
     else y = QINT ? double(int(short(k8 * q_int))) : double(k8) * qd;              // int16 * python int stays int16
@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(RdLayout<B>::NT, 3) rd_sweep_kernel(const RdAr
   const int nbx = min(TBX, g.nx - bx0);
   const bool do_hist = (a.flags & VCFB_F_HIST) != 0;
   const bool nowrap = (a.flags & VCFB_F_NOWRAP) != 0;
+  const int poff = (a.flags & VCFB_F_NO_OFFSET) ? 0 : 128;   // the loop of optimize_block_size runs without offset (vcfb200.h)
 
   for (int i = tid; i < 3 * 256 + MAXQ * 8; i += NT) shist[i] = 0;
 
@@ -164,9 +165,9 @@ __global__ void __launch_bounds__(RdLayout<B>::NT, 3) rd_sweep_kernel(const RdAr
       const uint8_t* px = raw + r * RAWP + x * 3;
       const int R = px[0], Gc = px[1], Bc = px[2];
       if (a.color == VCFB_COLOR_YCOCG) {
-        v[r] = float((c == 0) ? (R + 2 * Gc + Bc - 512) : (c == 1) ? (R - Bc) : (2 * Gc - R - Bc));
+        v[r] = float((c == 0) ? (R + 2 * Gc + Bc - 4 * poff) : (c == 1) ? (R - Bc) : (2 * Gc - R - Bc));
       } else {
-        const float r_ = float(R - 128), g_ = float(Gc - 128), b_ = float(Bc - 128);
+        const float r_ = float(R - poff), g_ = float(Gc - poff), b_ = float(Bc - poff);
         const float y = OF::add(OF::add(OF::mul(r_, 0.299f), OF::mul(g_, 0.587f)), OF::mul(b_, 0.114f));
         v[r] = c == 0 ? y : c == 1 ? OF::mul(OF::sub(r_, y), 0.713f) : OF::mul(OF::sub(b_, y), 0.564f);
       }
@@ -201,7 +202,7 @@ __global__ void __launch_bounds__(RdLayout<B>::NT, 3) rd_sweep_kernel(const RdAr
       unsigned* hc = shist + c * 256;
       // (lanes of blocks beyond the frame's right edge hold zero coefficients: they store zeros into their own
       //  part of the tile and count nothing)
-#define VCFB_RD_ROW(P2, QI, NW) quantise_row<B, P2, QI, NW>(coef, q, inv_q, q_int, qd, dst, hc, do_hist, nz, sabs)
+#define VCFB_RD_ROW(P2, QI, NW) quantise_row<B, P2, QI, NW>(coef, q, inv_q, q_int, qd, poff, dst, hc, do_hist, nz, sabs)
       if (nowrap) {
         if (pow2) { if (q_int) VCFB_RD_ROW(true, true, true); else VCFB_RD_ROW(true, false, true); }
         else      { if (q_int) VCFB_RD_ROW(false, true, true); else VCFB_RD_ROW(false, false, true); }
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(RdLayout<B>::NT, 3) rd_sweep_kernel(const RdAr
         if (sabs) atomicAdd(&sacc[qi * 8 + 1], sabs);
         if (do_hist) {
           const unsigned zeros = nlive * B - nz;
-          if (zeros) atomicAdd(&hc[128], zeros);
+          if (zeros) atomicAdd(&hc[poff], zeros);
         }
       }
     }
@@ -286,9 +287,10 @@ __global__ void __launch_bounds__(RdLayout<B>::NT, 3) rd_sweep_kernel(const RdAr
             Gv = OD::add(OD::add(c0, OD::mul(c1, -0.714)), OD::mul(c2, -0.344));
             Bv = OD::add(c0, OD::mul(c2, 1.773));
           }
-          const int v[3] = {min(max(__double2int_rz(OD::add(R, 128.0)), 0), 255),
-                            min(max(__double2int_rz(OD::add(Gv, 128.0)), 0), 255),
-                            min(max(__double2int_rz(OD::add(Bv, 128.0)), 0), 255)};
+          const double yoff = double(poff);
+          const int v[3] = {min(max(__double2int_rz(OD::add(R, yoff)), 0), 255),
+                            min(max(__double2int_rz(OD::add(Gv, yoff)), 0), 255),
+                            min(max(__double2int_rz(OD::add(Bv, yoff)), 0), 255)};
           const uint8_t* px = raw + r * RAWP + x * 3;
 #pragma unroll
           for (int k = 0; k < 3; ++k) {

@@ -178,9 +178,13 @@ class CoDec(CT.CoDec):
         return y, output_size
 
     def optimize_block_size(self):
-        '''src/2D-DCT.py:533-579 on the GPU: J = rate + Lambda*RMSE per block size, rate =
-        bytes of the entropy-coded indices, RMSE as the reference forms it (between the
-        image still shifted by 128 and the decoded image, :537,:572-574).'''
+        '''src/2D-DCT.py:533-579 on the GPU: J = rate + Lambda*RMSE per block size, rate = bytes of the
+        entropy-coded indices.  The loop body is reproduced as the reference RUNS it, not as it reads: it is
+        called from __init__ (:99-103) before ``self.offset = 128`` is assigned (:107-110), so ``self.offset`` still
+        is the [0, 0, 0] of the colour stage (src/YCoCg.py:28-29) -- no -128 on the pixels, no +128 on the
+        indices (VCFB_F_NO_OFFSET); the dequantiser gets the quantiser's own indices, never narrowed to uint8
+        (VCFB_F_NOWRAP, :565-568); neither -p nor -x applies (:540-556).  tests/golden/ref_flow_L_*.npz hold the
+        J values the unmodified reference logs; tests/test_plugin.py compares.'''
         logging.debug("trace")
         best = 1000000
         img = self.encode_read()
@@ -190,17 +194,13 @@ class CoDec(CT.CoDec):
             if img.shape[0] % block_size or img.shape[1] % block_size:
                 logging.warning(f"block_size={block_size} skipped (the reference applies no padding here)")
                 continue
-            enc = Codec(block_size=block_size, q=self.QSS)     # the loop knows neither -p nor -x (:540-556)
-            decom_k = enc.encode(img)
+            decom_k = Codec(block_size=block_size, q=self.QSS, no_offset=True).encode(img)       # :540-559
             decom_k_bytes = self.compress(decom_k)
             decom_k_bytes.seek(0)
             rate = len(decom_k_bytes.read())
-            # :565-573 -- the loop dequantises the quantiser's own indices (never narrowed to uint8, no int16,
-            # no perceptual weights): the fused sweep kernel with VCFB_F_NOWRAP, one step
-            st = stats_dict(rd_stats_fused(img, block_size, [self.QSS], nowrap=True, hist=False)[0].cpu().numpy())
-            n = st["nsamples"]
-            se = float(st["sse"].sum()) - 256.0 * st["sumdiff"] + 16384.0 * n   # sum((img-128) - y)^2
-            RMSE = float(np.sqrt(se / n))
+            st = stats_dict(rd_stats_fused(img, block_size, [self.QSS], nowrap=True, no_offset=True,
+                                           hist=False)[0].cpu().numpy())                        # :565-573
+            RMSE = float(np.sqrt(float(st["sse"].sum()) / st["nsamples"]))                       # :574
             J = rate + self.Lambda * RMSE
             logging.debug(f"J={J} for block_size={block_size}")
             if J < best:

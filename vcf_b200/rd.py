@@ -20,7 +20,8 @@ from . import _lib
 from .codec import Codec, _COLORS, _is_torch, stats_dict
 
 
-def rd_stats_fused(frames, block_size: int, qs, color: str = "YCoCg", nowrap: bool = False, hist: bool = True):
+def rd_stats_fused(frames, block_size: int, qs, color: str = "YCoCg", nowrap: bool = False, hist: bool = True,
+                   no_offset: bool = False):
     """Statistics vectors of every step in ``qs`` for one block size from ONE pass over ``frames``
     (vcfb_rd_sweep_dev, csrc/kernels_rd.cu): the forward transform runs once, each step is quantised,
     dequantised and decoded on chip, nothing but the int64 statistics is written.  Row i equals what
@@ -28,6 +29,8 @@ def rd_stats_fused(frames, block_size: int, qs, color: str = "YCoCg", nowrap: bo
 
     nowrap: the dequantiser sees the quantiser's own indices, not the ones wrapped to uint8 -- the
     in-process loop of src/2D-DCT.py:533-579 (optimize_block_size).
+    no_offset: neither -128 on the pixels nor +128 on the indices: that loop runs before ``self.offset = 128`` is
+    assigned (src/2D-DCT.py:99-110), with the [0, 0, 0] the colour stage left in ``self.offset`` (src/YCoCg.py:28-29).
     frames: CUDA uint8 tensor (n,H,W,3)|(H,W,3) (a numpy array is uploaded).  Returns an int64 tensor
     (len(qs), STAT_LEN) on the device."""
     import ctypes as C
@@ -43,7 +46,7 @@ def rd_stats_fused(frames, block_size: int, qs, color: str = "YCoCg", nowrap: bo
     x = x.contiguous()
     qs = [float(q) for q in qs]
     out = torch.zeros((len(qs), _lib.STAT_LEN), dtype=torch.int64, device=x.device)
-    flags = (_lib.F_HIST if hist else 0) | (_lib.F_NOWRAP if nowrap else 0)
+    flags = (_lib.F_HIST if hist else 0) | (_lib.F_NOWRAP if nowrap else 0) | (_lib.F_NO_OFFSET if no_offset else 0)
     n, H, W, _ = x.shape
     with torch.cuda.device(x.device):
         stream = torch.cuda.current_stream().cuda_stream
