@@ -49,6 +49,9 @@ CASES = [
     # reference's own debug log (:576).  Bright frames and a small step make the indices leave [-128, 127].
     ("L_q4_bright", 128, 128, "natural", 31, "2D-DCT.py", ["-L", "50", "-q", "4", "-g"]),
     ("L_q32", 128, 256, "natural", 32, "2D-DCT.py", ["-L", "2000", "-q", "32", "-g"]),
+    # -f: the decoder hands the UN-CLIPPED float64 image to the denoising filter of the class chain (:461) and clips
+    # afterwards (:466); src/gaussian_blur.py is cv2.GaussianBlur(y, (5, 5), 0).  Decode-only flag.
+    ("f_gaussian_q16", 72, 104, "natural", 33, "2D-DCT.py", ["-q", "16", "-f", "gaussian_blur"]),
 ]
 
 
@@ -86,7 +89,8 @@ def main():
                 if os.path.exists(f):
                     os.remove(f)
             shutil.copy(src, "/tmp/original.png")
-            log = run(script, "encode", flags + io_flags, env)
+            eflags = [f for i, f in enumerate(flags) if f != "-f" and (i == 0 or flags[i - 1] != "-f")]
+            log = run(script, "encode", eflags + io_flags, env)
             dflags = [f for i, f in enumerate(flags) if f not in ("-L", "-g") and (i == 0 or flags[i - 1] != "-L")]
             if "-L" in flags:        # the decoder does not know which block size the encoder chose (:64-66): tell it
                 chosen = int(log.split("optimal block_size=")[1].split()[0])

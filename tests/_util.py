@@ -21,6 +21,8 @@ def parse_flags(flags):
             i += 2   # block-size search: the chosen size is recorded with the vector (L_chosen)
         elif f == "-g":
             i += 1
+        elif f == "-f":
+            i += 2   # decode-side denoising filter: applied by the tests that know it (golden_filter)
         else:
             raise AssertionError(f)
     return kw
@@ -32,3 +34,9 @@ def golden_kw(g):
     if "L_chosen" in g.files:
         kw["B"] = int(g["L_chosen"])
     return kw
+
+
+def golden_filter(g):
+    """Name of the decode-side filter of a golden vector (src/deadzone.py:33), or None."""
+    flags = [str(f) for f in g["flags"]]
+    return flags[flags.index("-f") + 1] if "-f" in flags else None

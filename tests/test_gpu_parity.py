@@ -9,7 +9,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 from oracle import vcf_oracle as O
-from _util import golden_kw as _gkw, parse_flags as _parse
+from _util import golden_filter as _gfilter, golden_kw as _gkw, parse_flags as _parse
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -43,6 +43,14 @@ def test_reference_golden_bit_exact(fn, torch_cuda):
     assert np.array_equal(idx, g["idx"])               # reference's own float32 path
     c64 = _codec(block_size=kw["B"], q=kw["q"], perceptual=kw["perceptual"],
                  disable_subbands=kw["disable_subbands"], fp64=True)
+    if _gfilter(g) == "gaussian_blur":
+        # -f: the un-clipped float64 image goes through the chain's filter (src/2D-DCT.py:461, src/gaussian_blur.py)
+        import cv2
+        _, yf = c64.decode(g["idx"], g["img"].shape, return_float=True)
+        assert yf.dtype == np.float64
+        dec = np.clip(cv2.GaussianBlur(yf, (5, 5), 0), 0, 255).astype(np.uint8)
+        assert np.array_equal(dec, g["decoded"])
+        return
     dec = c64.decode(g["idx"], g["img"].shape)
     assert np.array_equal(dec, g["decoded"])           # reference's float64 decode chain
     # same through the torch / device-pointer entry points

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from oracle import vcf_oracle as O
-from _util import golden_kw, parse_flags as _parse
+from _util import golden_filter, golden_kw, parse_flags as _parse
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 FILES = sorted(glob.glob(os.path.join(GOLD, "ref_flow_*.npz")))
@@ -32,7 +32,14 @@ def test_oracle_matches_reference_flow(fn):
             k = O.encode_array(img, loop=loop, **kw)
             assert k.dtype == np.uint8 and k.shape == idx.shape
             assert np.array_equal(k, idx)
-            y = O.decode_array(idx, img.shape, loop=loop, **kw)
+            if golden_filter(g) == "gaussian_blur":
+                import cv2   # src/gaussian_blur.py: the filter gets the un-clipped float64 image (:461), the clip follows (:466)
+                yf = O.decode_array(idx, img.shape, loop=loop, return_float=True, **kw)
+                assert yf.dtype == np.float64
+                y = np.clip(cv2.GaussianBlur(yf, (5, 5), 0), 0, 255).astype(np.uint8)
+            else:
+                assert golden_filter(g) is None
+                y = O.decode_array(idx, img.shape, loop=loop, **kw)
             assert np.array_equal(y, dec)
     elif script == "YCoCg.py":
         assert np.array_equal(O.ycocg_standalone_encode(img, kw["q"]), idx)
