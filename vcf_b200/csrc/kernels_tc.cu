@@ -352,11 +352,16 @@ namespace enc {
 
 constexpr int RGB_TILE = 8 * TB * 24;      // two halves of [8 rows][64 blocks x 24 bytes] (two TMA boxes)
 constexpr int IDXT = 64 * TB * 3;          // [kk = 8u + v][128 blocks x 3 bytes]
-constexpr int NSIN = 3, NSOUT = 2;
+constexpr int NSIN = 3, NSOUT = 3;          // one output stage per epilogue group
 constexpr int NF = 80;                     // rows of the hi limb: 64 coefficients + 8 + 8 column sums
 constexpr int HI_BYTES = NF * 64 * 2, LO_BYTES = 64 * 64 * 2;
 constexpr int HI_LBO = NF / 8 * 128, LO_LBO = 1024;
 constexpr int ND = 4, NA = 6;
+// An increase is served from what the CTA's own warpgroups have handed back (not from registers the launch left
+// unused): at 80 registers per thread and 768 threads the converters (80 -> 64) and the service group (80 -> 24) free
+// 4 096 + 7 168, the three epilogue groups (80 -> 104) take 9 216.  (72 / 40 freed 7 168 < 9 216: the epilogue spun
+// in its allocation loop for ever.)
+constexpr int REGS_EPI = 104, REGS_CONV = 64, REGS_SERVICE = 24;
 constexpr int D_ITEM = NF, A_ITEM = 32;
 constexpr int A_COL0 = ND * D_ITEM;        // 320
 
@@ -364,13 +369,16 @@ constexpr int OFF_IN = 0;
 constexpr int OFF_OUTI = OFF_IN + NSIN * RGB_TILE;
 constexpr int OFF_F = OFF_OUTI + NSOUT * IDXT;
 constexpr int OFF_EBAR = OFF_F + HI_BYTES + LO_BYTES;
-constexpr int ESMEM = OFF_EBAR + 256;
+constexpr int ESMEM = OFF_EBAR + 512;
 
 struct EBars {
-  uint64_t in_full[NSIN], in_empty[NSIN], a_full[NA], a_empty[NA], d_full[ND], d_empty[ND], out_full[NSOUT], out_free[NSOUT];
+  // d_full is per (epilogue group, channel): every barrier then has ONE waiter that sees each of its phases in turn.
+  // (With a d_full per D slot, a third group starts in the middle of the item sequence and meets barriers that are two
+  // phases away from the one it last saw -- a parity wait cannot tell those apart, and the pipeline dead-locked.)
+  uint64_t in_full[NSIN], in_empty[NSIN], a_full[NA], a_empty[NA], d_full[3 * 3], d_empty[ND], out_full[NSOUT], out_free[NSOUT];
   uint32_t tmem_base;
 };
-static_assert(sizeof(EBars) <= 256, "barrier block");
+static_assert(sizeof(EBars) <= 512, "barrier block");
 
 struct TcEncArgs {
   int ntiles, tiles_x, ny, nx, top;
@@ -385,13 +393,24 @@ __device__ __forceinline__ unsigned pack_sat_s8(int a, int b, unsigned c) {
   return d;
 }
 
+// Registers follow the roles (setmaxnreg, one instruction per warpgroup): the three epilogue groups take what the
+// converter groups and the service group (TMA producer, MMA issuer, store warp and a fourth, idle warp that only
+// completes the warpgroup) hand back.
+#ifdef VCFB_NO_SETMAXNREG
+template <int N> __device__ __forceinline__ void reg_inc() {}
+template <int N> __device__ __forceinline__ void reg_dec() {}
+#else
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+#endif
+
 template <int NGE, int NGC>
-__global__ void __launch_bounds__((NGE + NGC) * 128 + 96, 1)
+__global__ void __launch_bounds__((NGE + NGC) * 128 + 128, 1)
 enc8_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
                const TcEncArgs a) {
-  constexpr int EPI_THREADS = NGE * 128, CONV_THREADS = NGC * 128, NTHREADS = EPI_THREADS + CONV_THREADS + 96;
+  constexpr int EPI_THREADS = NGE * 128, CONV_THREADS = NGC * 128, NTHREADS = EPI_THREADS + CONV_THREADS + 128;
   constexpr int W_CONV = EPI_THREADS / 32, W_TMA = (EPI_THREADS + CONV_THREADS) / 32, W_MMA = W_TMA + 1, W_ST = W_TMA + 2;
-  static_assert(NGE == 1 || NGE == 2, "epilogue groups take the tiles in turn; two output stages");
+  static_assert(NGE >= 1 && NGE <= 3, "epilogue groups take the tiles in turn (tile k: group k % NGE, output stage k % NSOUT)");
   static_assert(NGC == 1 || NGC == 2, "converter groups split the pixel rows 0-3 / 4-7");
   extern __shared__ __align__(128) unsigned char smem[];
   EBars* bars = reinterpret_cast<EBars*>(smem + OFF_EBAR);
@@ -408,10 +427,8 @@ enc8_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
       tma::mbar_init(&bars->a_full[s], 4 * NGC);
       tma::mbar_init(&bars->a_empty[s], 1);
     }
-    for (int s = 0; s < ND; ++s) {
-      tma::mbar_init(&bars->d_full[s], 1);
-      tma::mbar_init(&bars->d_empty[s], 4);
-    }
+    for (int s = 0; s < 9; ++s) tma::mbar_init(&bars->d_full[s], 1);
+    for (int s = 0; s < ND; ++s) tma::mbar_init(&bars->d_empty[s], 4);
     for (int s = 0; s < NSOUT; ++s) {
       tma::mbar_init(&bars->out_full[s], 4);
       tma::mbar_init(&bars->out_free[s], 1);
@@ -431,6 +448,8 @@ enc8_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
   const uint32_t tbase = *reinterpret_cast<volatile uint32_t*>(&bars->tmem_base);
   const int per_frame = a.ny * a.tiles_x;
 
+  if (warp >= W_TMA) {
+  reg_dec<REGS_SERVICE>();   // the service warpgroup: TMA producer, store warp, MMA issuer, one idle warp
   if (warp == W_TMA) {
     // ===== TMA producer of RGB tiles (zero padding = out-of-bounds fill; rows may start above the frame) =====
     if (lane == 0) {
@@ -450,8 +469,8 @@ enc8_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
     if (lane == 0) {
       int k = 0;
       for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++k) {
-        const int st = k & 1;
-        tc::mbar_wait_sleep(&bars->out_full[st], (k >> 1) & 1, 100);
+        const int st = k % NSOUT;
+        tc::mbar_wait_sleep(&bars->out_full[st], (k / NSOUT) & 1, 100);
         const int f = tile / per_frame, rem = tile - f * per_frame, by = rem / a.tiles_x, tx = rem - by * a.tiles_x;
         tma::store_5d(&out_map, smem + OFF_OUTI + st * IDXT, tx * (TB * 3 / 4), 0, by, 0, f);
         tma::commit_group();
@@ -469,8 +488,8 @@ enc8_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
       const uint32_t f_base = tma::smem_u32(smem + OFF_F);
       const uint32_t tb_u = __shfl_sync(0xffffffffu, tbase, 0);
       TCP_ON(long long eprof[2] = {0, 0}; const long long te0 = clock64();)
-      int it = 0;                            // item = (tile, channel)
-      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+      int it = 0, kt = 0;                    // item = (tile, channel); kt = tiles done
+      for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++kt) {
 #pragma unroll
         for (int c = 0; c < 3; ++c, ++it) {
           const int sa = it % NA, sd = it % ND;
@@ -489,14 +508,16 @@ enc8_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
             for (int ks = 0; ks < 4; ++ks)
               tc::mma_ts(d_t, a_t + ks * 8, tc::smem_desc(f_base + HI_BYTES + ks * 2 * LO_LBO, LO_LBO, 128), IDESC_LO, 1u);
             tc::commit(&bars->a_empty[sa]);
-            tc::commit(&bars->d_full[sd]);
+            tc::commit(&bars->d_full[(kt % NGE) * 3 + c]);
           }
           __syncwarp();
         }
       }
       TCP_ON(if (a.prof && blockIdx.x == 0 && lane == 0) { a.prof[0] = clock64() - te0; a.prof[1] = eprof[0]; a.prof[2] = eprof[1]; })
     }
+  }
   } else if (warp >= W_CONV) {
+    reg_dec<REGS_CONV>();
     // ===== converter: thread = (block, 8 / NGC pixel rows) =====
     const int b = threadIdx.x & 127, grp = (warp - W_CONV) >> 2;
     const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
@@ -555,6 +576,7 @@ enc8_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
     }
     TCP_ON(if (a.prof && blockIdx.x == 0 && threadIdx.x == W_CONV * 32) { a.prof[8] = clock64() - tcv0; a.prof[9] = cw[0]; a.prof[10] = cw[1]; a.prof[11] = cw[2]; })
   } else {
+    reg_inc<REGS_EPI>();
     // ===== epilogue: thread = block = TMEM lane; the NGE warp groups take the tiles in turn, so the latency of a
     // tile's chain (barrier -> tensor-memory load -> quantise -> shuffle -> store) is hidden behind the other group =====
     const int b = threadIdx.x & 127, grp = warp >> 2;
@@ -567,7 +589,7 @@ enc8_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
     int k = 0;
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++k) {
       if (k % NGE != grp) continue;
-      const int st = k & 1, ku = k / NGE;                // ku: how many tiles this group has done
+      const int st = k % NSOUT, ku = k / NGE;            // ku: how many tiles this group has done
       uint32_t hold[3][2][4][2];                         // [channel][half][row][4 index bytes each]
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
@@ -575,7 +597,7 @@ enc8_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
         // coefficient = D / (4096 * colour scale): the converter fed 4Y, 2Co, 4Cg
         const float sc = a.inv_q * (c == 1 ? 0x1p-13f : 0x1p-14f);
         TCP_ON(const long long tq0 = clock64();)
-        tc::mbar_wait(&bars->d_full[sd], (it / ND) & 1);
+        tc::mbar_wait(&bars->d_full[grp * 3 + c], ku & 1);
         TCP_ON(pw[0] += clock64() - tq0;)
         tc::fence_after();
         const uint32_t dcol = tbase + lane_off + sd * D_ITEM;
@@ -630,7 +652,7 @@ enc8_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
       }
       // ---- the three channels of the block are in registers: write rows [8u + v][3 block + channel] as words ----
       TCP_ON(const long long tq1 = clock64();)
-      tc::mbar_wait(&bars->out_free[st], ((k >> 1) & 1) ^ 1);       // the store that last read this stage is done
+      tc::mbar_wait(&bars->out_free[st], ((k / NSOUT) & 1) ^ 1);    // the store that last read this stage is done
       TCP_ON(const long long tq2 = clock64(); pw[1] += tq2 - tq1;)
       uint32_t* ow = reinterpret_cast<uint32_t*>(smem + OFF_OUTI + st * IDXT) + 3 * (b >> 2) + qj;
 #pragma unroll
@@ -851,10 +873,8 @@ int launch_encode_tc(const EncArgs& a, cudaStream_t s) {
   void (*kern)(const CUtensorMap, const CUtensorMap, const enc::TcEncArgs);
   int nthreads;
   switch (cfg) {
-    case 21: kern = enc::enc8_tc_kernel<2, 1>; nthreads = 3 * 128 + 96; break;
-    case 12: kern = enc::enc8_tc_kernel<1, 2>; nthreads = 3 * 128 + 96; break;
-    case 11: kern = enc::enc8_tc_kernel<1, 1>; nthreads = 2 * 128 + 96; break;
-    default: kern = enc::enc8_tc_kernel<2, 2>; nthreads = 4 * 128 + 96; break;      // measured fastest (0.66 ms per 64 4K noise frames)
+    case 22: kern = enc::enc8_tc_kernel<2, 2>; nthreads = 4 * 128 + 128; break;
+    default: kern = enc::enc8_tc_kernel<3, 2>; nthreads = 5 * 128 + 128; break;
   }
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, enc::ESMEM);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(enc8_tc)");

@@ -3,6 +3,7 @@
 // SmemDescriptor) and cute/atom/mma_traits_sm100.hpp (canonical no-swizzle layouts); they were
 // checked on the hardware with profiles/microbench/tc_bringup.cu before anything was built on them.
 #pragma once
+#include <stdio.h>
 
 #include <stdint.h>
 
@@ -18,6 +19,27 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // Wait for the phase with this parity.  try_wait suspends the warp in hardware for up to the hinted time
 // instead of spinning: a polling warp takes issue slots from the warps that do the work (ncu on the first
 // version of kernels_tc.cu: 83 % of the issue slots busy, half of them in wait loops).
+#ifdef VCFB_TC_WATCHDOG
+// Debug build: a wait that does not complete within ~0.2 s reports itself and returns, so that a dead-locked
+// pipeline terminates (with garbage) and its printf buffer shows who waited for what.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (int spin = 0; spin < 2000; ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(done)
+        : "r"(tma::smem_u32(bar)), "r"(parity), "r"(100000u)
+        : "memory");
+    if (done) return;
+  }
+  if ((threadIdx.x & 31) == 0 && blockIdx.x == 0)
+    printf("[watchdog] warp %d stuck on barrier at smem offset %u parity %u\n", int(threadIdx.x >> 5), tma::smem_u32(bar), parity);
+}
+#else
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
@@ -30,7 +52,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 // for the latency-insensitive control warps: back off between polls
+#endif
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, unsigned ns) {
+#ifdef VCFB_TC_WATCHDOG
+  (void)ns;
+  mbar_wait(bar, parity);
+  return;
+#endif
   uint32_t done;
   do {
     asm volatile(
