@@ -119,6 +119,16 @@ def test_fast_encoder_statistics_and_host_api():
     assert s["nonzero"] == int((k != 0).sum()) and s["sumabs"] == int(np.abs(k).sum()) and s["nindices"] == k.size
     host = c.encode(img)
     assert np.array_equal(host, idx.cpu().numpy())
+    # without the histogram the sums come out of the encoder's epilogue (no second pass): frames whose last tile of a
+    # block row is partial (1152 / 8 = 144 blocks = 128 + 16), vertical padding, a batch
+    for H, W, n in ((120, 1024, 1), (100, 1152, 3), (64, 2048, 2)):
+        frames = np.stack([O.synthetic_frame(H, W, 90 + i, "noise" if i % 2 else "natural") for i in range(n)])
+        launches0 = _lib.launch_count()
+        idx2, st2 = _codec(block_size=8, q=8, fast=True, hist=False).encode(torch.from_numpy(frames).cuda(), stats=True)
+        assert _lib.last_kernel() == "enc8_tc" and _lib.launch_count() - launches0 <= 2      # encoder + the index count
+        k2 = idx2.cpu().numpy().astype(np.int16) - 128
+        s2 = stats_dict(st2.cpu().numpy())
+        assert s2["nonzero"] == int((k2 != 0).sum()) and s2["sumabs"] == int(np.abs(k2).sum()) and s2["nindices"] == k2.size, (H, W)
     # round trip in fast mode stays within +-1 LSB of the reference's round trip
     ref = O.decode_array(O.encode_array(img, 8, 16), img.shape, 8, 16)
     dec = c.decode(idx, img.shape[:2]).cpu().numpy()

@@ -116,9 +116,14 @@ int vcfb_encode_dev(const uint8_t* rgb, int n_frames, int H, int W, int B, doubl
     // fast mode: tensor-core encoder; statistics, when asked for, by the streaming pass over the indices
     static const bool tc_off = getenv("VCFB_TC") && getenv("VCFB_TC")[0] == '0';
     if (!tc_off) {
-      rc = launch_encode_tc(a, static_cast<cudaStream_t>(cuda_stream));
-      if (rc == VCFB_OK && a.stats)
-        rc = launch_index_stats(a.idx, (long long)n_frames * a.g.Hp * a.g.Wp * 3, (flags & VCFB_F_HIST) != 0, a.stats,
+      // statistics: the sums come out of the encoder's epilogue; the histogram, when asked for, takes the streaming
+      // pass over the stored indices (kernels_stats.cu)
+      const bool hist = a.stats && (flags & VCFB_F_HIST);
+      EncArgs t = a;
+      if (hist) t.stats = nullptr;
+      rc = launch_encode_tc(t, static_cast<cudaStream_t>(cuda_stream));
+      if (rc == VCFB_OK && hist)
+        rc = launch_index_stats(a.idx, (long long)n_frames * a.g.Hp * a.g.Wp * 3, true, a.stats,
                                 static_cast<cudaStream_t>(cuda_stream));
       if (rc != VCFB_E_UNSUPP) return rc;
     }

@@ -385,6 +385,7 @@ struct TcEncArgs {
   float inv_q;                             // 1 / q, q a power of two
   const unsigned char* ftab;               // HI_BYTES + LO_BYTES, canonical layout
   long long* prof;
+  unsigned long long* stats;               // STATS: VCFB_STAT_NONZERO / VCFB_STAT_SUMABS accumulated in the epilogue
 };
 
 __device__ __forceinline__ unsigned pack_sat_s8(int a, int b, unsigned c) {
@@ -404,7 +405,7 @@ template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setma
 template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
 #endif
 
-template <int NGE, int NGC>
+template <int NGE, int NGC, bool STATS = false>
 __global__ void __launch_bounds__((NGE + NGC) * 128 + 128, 1)
 enc8_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant__ CUtensorMap out_map,
                const TcEncArgs a) {
@@ -586,6 +587,7 @@ enc8_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
     const int qj = lane & 3;                             // lane j < 3 of the quad writes word j
     const uint32_t wsel = qj == 0 ? 0x4210u : (qj == 1 ? 0x5421u : 0x6542u);
     TCP_ON(long long pw[3] = {0, 0, 0}; const long long tp0 = clock64();)
+    unsigned st_nz = 0, st_abs = 0;                     // STATS: non-zero indices and sum |index| of this thread's blocks
     int k = 0;
     for (int tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x, ++k) {
       if (k % NGE != grp) continue;
@@ -672,7 +674,34 @@ enc8_tc_kernel(const __grid_constant__ CUtensorMap in_map, const __grid_constant
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&bars->out_full[st]);
       TCP_ON(pw[2] += clock64() - tq2;)
+      if (STATS) {
+        // the index bytes of this block are still in registers (byte = index + 128): |index| by a byte-wise absolute
+        // difference, the count of non-zero ones by a byte-wise compare, both summed with dp4a.  Blocks beyond the
+        // right edge of the frame (partial last tile: computed from zero fill, never stored) do not count.
+        const int tx = tile % a.tiles_x;
+        if (tx * TB + b < a.nx) {
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+#pragma unroll
+              for (int ur = 0; ur < 4; ++ur)
+#pragma unroll
+                for (int w = 0; w < 2; ++w) {
+                  const uint32_t v = hold[c][h][ur][w];
+                  st_abs = __dp4a(__vabsdiffu4(v, 0x80808080u), 0x01010101u, st_abs);
+                  st_nz = __dp4a(__vsetne4(v, 0x80808080u), 0x01010101u, st_nz);
+                }
+        }
+      }
       (void)ku;
+    }
+    if (STATS) {
+      const unsigned nzw = __reduce_add_sync(0xffffffffu, st_nz), absw = __reduce_add_sync(0xffffffffu, st_abs);
+      if (lane == 0) {
+        if (nzw) atomicAdd(a.stats + VCFB_STAT_NONZERO, (unsigned long long)nzw);
+        if (absw) atomicAdd(a.stats + VCFB_STAT_SUMABS, (unsigned long long)absw);
+      }
     }
     TCP_ON(if (a.prof && blockIdx.x == 0 && threadIdx.x == 0) { a.prof[4] = clock64() - tp0; a.prof[5] = pw[0]; a.prof[6] = pw[1]; a.prof[7] = pw[2]; })
   }
@@ -862,6 +891,7 @@ int launch_encode_tc(const EncArgs& a, cudaStream_t s) {
   ta.inv_q = float(a.inv_q);
   ta.ftab = ftab;
   ta.prof = nullptr;
+  ta.stats = a.stats;                      // non-NULL only when the caller wants the sums without the histogram (api.cu)
 #ifdef VCFB_TC_PROFILE
   static long long* eprof_buf = nullptr;
   if (!eprof_buf) cudaMalloc(reinterpret_cast<void**>(&eprof_buf), 128);
@@ -872,9 +902,16 @@ int launch_encode_tc(const EncArgs& a, cudaStream_t s) {
   const int cfg = dev_cfg("VCFB_TC_ENC_CFG");
   void (*kern)(const CUtensorMap, const CUtensorMap, const enc::TcEncArgs);
   int nthreads;
-  switch (cfg) {
-    case 22: kern = enc::enc8_tc_kernel<2, 2>; nthreads = 4 * 128 + 128; break;
-    default: kern = enc::enc8_tc_kernel<3, 2>; nthreads = 5 * 128 + 128; break;
+  if (cfg == 22 && !a.stats) {
+    kern = enc::enc8_tc_kernel<2, 2>;
+    nthreads = 4 * 128 + 128;
+  } else {
+    kern = a.stats ? enc::enc8_tc_kernel<3, 2, true> : enc::enc8_tc_kernel<3, 2>;
+    nthreads = 5 * 128 + 128;
+  }
+  if (a.stats) {
+    const int rc = launch_add_count(a.stats, VCFB_STAT_NINDICES, (unsigned long long)a.n_frames * g.Hp * g.Wp * 3, s);
+    if (rc) return rc;
   }
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, enc::ESMEM);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(enc8_tc)");
