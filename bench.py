@@ -837,9 +837,11 @@ def entropy_stage(cx, a, wl):
         out = {"codec": "zlib level 6 on one frame of indices (q=%d), 1 host core" % q_ent,
                "mpixel_s": H * W / 1e6 / dt, "bits_per_pixel": 8.0 * len(comp) / (H * W),
                "note": "not part of `value` or `e2e`; the reference's containers (TIFF/PNG/npz) wrap the same deflate"}
-        kb = codec.encode(x).reshape(-1)
-        dst, nb = deflate_raw_dev(kb)           # warm-up, and the stream that is checked
-        one, nb1 = deflate_raw_dev(kb[: k.size])
+        kx = codec.encode(x)
+        geom = (kx.shape[2] * kx.shape[3], kx.shape[3])      # bytes per row and per pixel of the H x W x 3 index image
+        kb = kx.reshape(-1)
+        dst, nb = deflate_raw_dev(kb, geom)           # warm-up, and the stream that is checked
+        one, nb1 = deflate_raw_dev(kb[: k.size], geom)
         torch.cuda.synchronize()
         ok = zlib.decompress(one[: int(nb1.item())].cpu().numpy().tobytes(), -15) == k.tobytes()
         L_ = _L.lib()
@@ -848,13 +850,14 @@ def entropy_stage(cx, a, wl):
         reps = 10
         e0.record()
         for _ in range(reps):
-            _L.check(L_.vcfb_deflate_dev(kb.data_ptr(), kb.numel(), dst.data_ptr(), dst.numel(), nb.data_ptr(),
-                                         ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream))
+            _L.check(L_.vcfb_deflate_rows_dev(kb.data_ptr(), kb.numel(), geom[0], geom[1], dst.data_ptr(), dst.numel(),
+                                              nb.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream))
         e1.record()
         torch.cuda.synchronize()
         gms = e0.elapsed_time(e1) / reps
         out["gpu_deflate"] = {
-            "api": "vcfb_deflate_dev, %d frames of indices per call, in HBM" % nf,
+            "api": "vcfb_deflate_rows_dev (runs + previous sample + samples above as match candidates), %d frames of indices per call, in HBM" % nf,
+            "size_vs_zlib6_one_frame": int(nb1.item()) / len(comp),
             "ms_per_call": gms, "mpixel_s": nf * H * W / 1e6 / (gms / 1e3), "input_GB_s": kb.numel() / 1e9 / (gms / 1e3),
             "bits_per_pixel": 8.0 * int(nb.item()) / (nf * H * W),
             "bits_per_pixel_one_frame": 8.0 * int(nb1.item()) / (H * W),

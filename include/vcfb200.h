@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define VCFB_VERSION 140 /* 0.4.0: + vcfb_rd_sweep_dev, VCFB_F_NOWRAP, block sizes 2 / 64 / 128; 0.3.0: + VCFB_F_SYNTH_F32; 0.2.0: + vcfb_deflate_dev, vcfb_deflate_bound, vcfb_deflate_workspace, vcfb_crc32_dev, vcfb_adler32_dev (0.1.1: vcfb_launch_count, motion estimation) */
+#define VCFB_VERSION 150 /* 0.5.0: + vcfb_deflate_rows_dev (row-above / previous-sample match candidates, cost model); 0.4.0: + vcfb_rd_sweep_dev, VCFB_F_NOWRAP, block sizes 2 / 64 / 128; 0.3.0: + VCFB_F_SYNTH_F32; 0.2.0: + vcfb_deflate_dev, vcfb_deflate_bound, vcfb_deflate_workspace, vcfb_crc32_dev, vcfb_adler32_dev (0.1.1: vcfb_launch_count, motion estimation) */
 
 /* error codes */
 #define VCFB_OK 0
@@ -205,8 +205,9 @@ int vcfb_block_match_tss_dev(const uint8_t* ref, const uint8_t* cur, int n_frame
 /* Entropy front-end: raw deflate (RFC 1951) of a byte array -- the zlib call
  * underneath the reference's entropy stage for the uint8 index planes (np.savez_compressed in
  * src/z_lib.py:19-23; tifffile's zlib codec in src/TIFF.py:23-31).  Run-length parse (distance-1
- * matches, zlib's Z_RLE strategy) + one dynamic Huffman block per segment of 132-528 KB, stored
- * blocks where those are smaller.  The stream is complete (last block has BFINAL = 1) and any
+ * matches, zlib's Z_RLE strategy, each taken only where a sampled cost model says it is cheaper than
+ * its bytes as literals) + one dynamic Huffman block per segment of 132 KB, stored blocks where
+ * those are smaller.  The stream is complete (last block has BFINAL = 1) and any
  * inflate implementation reads it: zlib.decompress(stream, -15); prefix 78 9C and append the
  * big-endian Adler-32 for a zlib stream; wrap in a zip member with its CRC-32 for .npz.
  * It is NOT byte-identical with zlib's output -- the property kept is that the reference's decoder
@@ -214,12 +215,25 @@ int vcfb_block_match_tss_dev(const uint8_t* ref, const uint8_t* cur, int n_frame
  * src        n_bytes bytes, device, 8-byte aligned
  * dst        device, dst_capacity >= vcfb_deflate_bound(n_bytes)
  * out_bytes  one uint64 on the device: length of the stream in dst
- * workspace  device, 16-byte aligned, >= vcfb_deflate_workspace(n_bytes) bytes (about n_bytes)
+ * workspace  device, 16-byte aligned, >= vcfb_deflate_workspace(n_bytes) bytes (about 3 * n_bytes:
+ *            the segments' streams before they are packed, and 16 bits per byte for the tokens)
  * Asynchronous on cuda_stream; three kernels (segments, scan, gather). */
 size_t vcfb_deflate_bound(size_t n_bytes);
 size_t vcfb_deflate_workspace(size_t n_bytes);
 int vcfb_deflate_dev(const uint8_t* src, size_t n_bytes, uint8_t* dst, size_t dst_capacity,
                      uint64_t* out_bytes, void* workspace, size_t workspace_bytes, void* cuda_stream);
+
+/* The same for an array of rows: src is rows of row_bytes bytes whose samples lie sample_bytes
+ * apart (the H x W x 3 uint8 index image the reference's entropy stage receives --
+ * src/z_lib.py:19-23, src/TIFF.py:23-31 -- has row_bytes = 3 * W, sample_bytes = 3).  Besides runs
+ * the parse then tries the previous sample of the same channel and the three samples above the
+ * current one (distances sample_bytes, row_bytes, row_bytes -+ sample_bytes: where zlib's hash
+ * chains find most of their matches in such planes) and takes a match when the cost model puts it
+ * below the run-length parse of the bytes it covers.  Candidate distances beyond deflate's 32 KB
+ * window are dropped; row_bytes = 0 is vcfb_deflate_dev.  Same buffers, bound and workspace. */
+int vcfb_deflate_rows_dev(const uint8_t* src, size_t n_bytes, size_t row_bytes, int sample_bytes, uint8_t* dst,
+                          size_t dst_capacity, uint64_t* out_bytes, void* workspace, size_t workspace_bytes,
+                          void* cuda_stream);
 
 /* CRC-32 (zip / zlib / PNG polynomial, the value zlib.crc32 returns) of n_bytes bytes on the device:
  * the checksum a zip member carries next to its deflate stream (np.savez_compressed,

@@ -5,6 +5,7 @@
 // parsing / Huffman / header / bit-packing logic is checked against zlib's decoder on machines
 // without a GPU.  Nothing in vcf_b200/ uses it.
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -14,15 +15,43 @@
 
 using namespace vcfb;
 
-extern "C" long long dfl_emul(const uint8_t* src, long long n, int piece, int NT, uint8_t* dst, long long cap,
-                              long long* n_stored_segments) {
+namespace {
+struct Store {                 // token j of a thread, laid out like the kernel's scratch (j-major)
+  uint16_t* base;
+  int NT;
+  void operator()(int j, uint16_t t) const { base[(long long)j * NT] = t; }
+};
+
+struct SampleAdd {
+  uint32_t* cnt;
+  uint32_t* tot;               // [0] literals, [1] run starts
+  void lit(int b) { ++cnt[b]; ++tot[0]; }
+  void run() { ++tot[1]; }
+};
+}  // namespace
+
+// row, pixel: make_match_params(); dists: overrides the candidate distances of the parse (nd of them, the
+// first one 1) when nd > 0.  model = 0: plain run-length parse (no cost model; runs only).
+extern "C" long long dfl_emul(const uint8_t* src, long long n, int piece, int NT, long long row, int pixel, const int* dists,
+                              int nd, int model, uint8_t* dst, long long cap, long long* n_stored_segments) {
+  dfl::MatchParams P = dfl::make_match_params(row, pixel);
+  if (nd > 0) {
+    P.nd = 1;
+    for (int i = 1; i < nd; ++i) dfl::match_params_add(P, dists[i], dfl::FAR_MIN);
+  }
+  if (!model) P.nd = 1;
+  if (const char* e = getenv("DFL_MARGIN8")) P.margin8 = atoi(e);
+  if (const char* e = getenv("DFL_PATIENCE")) P.patience = atoi(e);
+  if (const char* e = getenv("DFL_DCOST")) for (int i = 1; i < P.nd; ++i) P.dcost8[i] = uint8_t(P.dcost8[i] + atoi(e));
+  std::vector<uint16_t> tokens((size_t)NT * piece);
+  std::vector<int> ntok(NT);
   const long long seg_bytes = (long long)NT * piece;
   const long long nsegs = (n + seg_bytes - 1) / seg_bytes;
   const long long stride = (dfl::stored_size(seg_bytes) + 15) / 16 * 16 + 16;
   std::vector<uint8_t> region(stride);
   long long pos = 0, stored_count = 0;
   for (long long seg = 0; seg < nsegs; ++seg) {
-    uint32_t hist[288];
+    uint32_t hist[288], dhist[32];
     dfl::Codes codes;
     dfl::Header hdr;
     dfl::BuildScratch scratch;
@@ -32,12 +61,30 @@ extern "C" long long dfl_emul(const uint8_t* src, long long n, int piece, int NT
     auto S = [&](int tid) { return std::min(n, s0 + (long long)tid * piece); };
     auto E = [&](int tid) { return std::min(n, S(tid) + piece); };
     for (int i = 0; i < 288; ++i) hist[i] = 0;
+    for (int i = 0; i < 32; ++i) dhist[i] = 0;
     hist[dfl::EOB] = 1;
+    dfl::CostModel cm;
+    if (model) {
+      uint32_t cnt[256] = {0}, tot[2] = {0, 0};
+      SampleAdd add{cnt, tot};
+      for (int tid = 0; tid < NT; ++tid) dfl::sample_segment(src, n, s0, nseg, tid, NT, add);
+      for (int b = 0; b < 256; ++b) cm.lit8[b] = dfl::model_lit8(cnt, tot[0], tot[1], b);
+      cm.len8 = dfl::model_len8(tot[0], tot[1]);
+    }
     for (int tid = 0; tid < NT; ++tid) {
-      dfl::CountVisitor cv;
-      cv.init(hist);
-      dfl::parse_piece(src, n, S(tid), E(tid), cv);
-      cv.flush();
+      dfl::TokenVisitor<Store> tv;
+      tv.st.base = tokens.data() + tid;
+      tv.st.NT = NT;
+      tv.n = 0;
+      tv.cv.init(hist, dhist, &P);
+      dfl::parse_piece(src, n, S(tid), E(tid), P, model ? &cm : nullptr, tv);
+      tv.cv.flush();
+      ntok[tid] = tv.n;
+      if (tv.n > piece) return -6;
+    }
+    {
+      dfl::BuildScratch sd;
+      dfl::distance_code(dhist, sd, codes);
     }
     // the kernel's CTA-parallel construction, one step after the other ...
     scratch.m = 0;
@@ -52,7 +99,7 @@ extern "C" long long dfl_emul(const uint8_t* src, long long n, int piece, int NT
     dfl::segment_header(scratch, codes, hdr);
     {
       // ... gives the code of the serial build_code()
-      dfl::Codes c2;
+      dfl::Codes c2 = codes;
       dfl::Header h2;
       dfl::BuildScratch s2;
       int hi = 0;
@@ -64,9 +111,10 @@ extern "C" long long dfl_emul(const uint8_t* src, long long n, int piece, int NT
     }
     for (int tid = 0; tid < NT; ++tid) {
       dfl::SizeVisitor sv;
-      sv.len = codes.len;
+      sv.c = &codes;
+      sv.P = &P;
       sv.bits = 0;
-      dfl::parse_piece(src, n, S(tid), E(tid), sv);
+      for (int j = 0; j < ntok[tid]; ++j) dfl::visit_token(tokens[(size_t)j * NT + tid], sv);
       off[tid] = sv.bits;
     }
     long long acc = hdr.bits;
@@ -92,8 +140,9 @@ extern "C" long long dfl_emul(const uint8_t* src, long long n, int piece, int NT
         if (tid == 0) dfl::header_emit(hdr, bw);
         dfl::EmitVisitor ev;
         ev.c = &codes;
+        ev.P = &P;
         ev.bw = &bw;
-        dfl::parse_piece(src, n, S(tid), E(tid), ev);
+        for (int j = 0; j < ntok[tid]; ++j) dfl::visit_token(tokens[(size_t)j * NT + tid], ev);
         if (tid == 0 && bw.bitpos() != (NT > 1 ? (long long)off[1] : bw.bitpos()) && S(1) < E(1)) return -2;
         if (tid == NT - 1) {
           dfl::segment_close(codes, bw);

@@ -34,7 +34,7 @@ def test_header_symbols_exported(lib):
 
 def test_version_and_geometry(lib):
     from vcf_b200 import _lib
-    assert _lib.lib().vcfb_version() == 140
+    assert _lib.lib().vcfb_version() == 150
     assert _lib.padded_dims(2160, 3840, 32) == (2176, 3840, 8, 0)
     assert _lib.padded_dims(53, 37, 8) == (56, 40, 1, 1)
     assert _lib.padded_dims(1080, 1920, 16) == (1088, 1920, 4, 0)

@@ -22,15 +22,18 @@ def emul():
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-x", "c++", "-shared", "-fPIC", "-o", SO, SRC])
     L = ctypes.CDLL(SO)
     L.dfl_emul.restype = ctypes.c_longlong
-    L.dfl_emul.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
-                           ctypes.c_longlong, ctypes.POINTER(ctypes.c_longlong)]
+    L.dfl_emul.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_int, ctypes.c_longlong,
+                           ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong,
+                           ctypes.POINTER(ctypes.c_longlong)]
 
-    def run(data: np.ndarray, piece=258, nt=512):
+    def run(data: np.ndarray, piece=258, nt=512, row=0, pixel=1, dists=None, model=1):
         data = np.ascontiguousarray(data, dtype=np.uint8).ravel()
         cap = data.size + data.size // 1000 + 5 * (data.size // (piece * nt) + 2) * (piece * nt // 65535 + 2) + 64
         out = np.empty(cap, np.uint8)
         ns = ctypes.c_longlong(0)
-        n = L.dfl_emul(data.ctypes.data, data.size, piece, nt, out.ctypes.data, cap, ctypes.byref(ns))
+        d = np.asarray(dists if dists is not None else [], np.int32)
+        n = L.dfl_emul(data.ctypes.data, data.size, piece, nt, row, pixel, d.ctypes.data, d.size, model, out.ctypes.data,
+                       cap, ctypes.byref(ns))
         assert n > 0, f"emulation failed: {n}"
         return out[:n].tobytes(), ns.value
     return run
@@ -58,6 +61,53 @@ def test_index_planes_roundtrip_and_size(emul):
         assert size <= 1.30 * ref + 100 * nseg, (q, size, ref)        # and close to zlib's default
 
 
+def test_row_candidates_size(emul):
+    """With the row geometry of the H x W x 3 index image (the previous sample of the channel and the
+    samples above as match candidates, cost model on) the stream is never larger than the run-length
+    parse and close to zlib level 6 (1080p: 1.03 / 1.11 / 1.09 / 1.05 x at q = 8 / 16 / 32 / 64,
+    profiles/r2_deflate_candidates.json)."""
+    from oracle import vcf_oracle as O
+    img = O.synthetic_frame(540, 960, 2, "natural")
+    for q in (8, 16, 32, 64):
+        idx = O.encode_array(img, 8, q)
+        row, px = idx.shape[1] * idx.shape[2], idx.shape[2]
+        plain, _ = _roundtrip(emul, idx, model=0)
+        runs, _ = _roundtrip(emul, idx)
+        rows, _ = _roundtrip(emul, idx, row=row, pixel=px)
+        ref = len(zlib.compress(idx.tobytes(), 6))
+        assert runs <= plain + 64, (q, runs, plain)
+        assert rows <= runs + 64, (q, rows, runs)
+        assert rows <= 1.16 * ref, (q, rows, ref)
+    noise = O.encode_array(O.synthetic_frame(272, 480, 3, "noise"), 8, 32)
+    rows, _ = _roundtrip(emul, noise, row=noise.shape[1] * 3, pixel=3)
+    assert rows <= len(zlib.compress(noise.tobytes(), 6))
+
+
+def test_row_candidates_fuzz(emul):
+    """Periodic and repeated-row inputs at every kind of row length (shorter than a match, longer than
+    a piece, beyond the 32 KB window), matches that overlap their source, sources in the previous
+    segment."""
+    rng = np.random.default_rng(21)
+    for it in range(80):
+        row = int(rng.choice([1, 2, 3, 5, 7, 48, 255, 258, 300, 777, 5760, 32765, 32767, 32768, 40000]))
+        px = int(rng.choice([1, 1, 2, 3, 4]))
+        nrows = int(rng.integers(1, max(2, 120000 // row)))
+        k = int(rng.integers(1, 40))
+        base = rng.choice(k, size=row, p=rng.dirichlet(np.full(k, 0.4))).astype(np.uint8)
+        rows = np.tile(base, (nrows, 1))
+        flips = rng.random(rows.shape) < float(rng.choice([0.0, 0.002, 0.05, 0.5]))
+        rows[flips] = rng.integers(0, 256, int(flips.sum()), dtype=np.uint8)
+        if it % 4 == 0:
+            rows = np.cumsum(rows, axis=0, dtype=np.uint8)      # rows that differ from the one above
+        data = rows.ravel()[: int(rng.integers(1, rows.size + 1))]
+        piece = int(rng.choice([8, 64, 258, 258, 516]))
+        nt = int(rng.choice([1, 3, 32, 512]))
+        _roundtrip(emul, data, piece=piece, nt=nt, row=row, pixel=px)
+    for dists in ([1, 2], [1, 4, 5, 6, 7, 8, 9, 10], [1, 32768], [1, 32769, 40000]):
+        data = np.tile(rng.integers(0, 5, 33000, dtype=np.uint8), 3)
+        _roundtrip(emul, data, dists=dists)
+
+
 def test_edge_cases(emul):
     rng = np.random.default_rng(7)
     cases = [
@@ -79,6 +129,8 @@ def test_edge_cases(emul):
     for piece, nt in ((258, 512), (16, 4), (8, 3), (1032, 512), (516, 512), (256, 512)):
         for data in cases:
             _roundtrip(emul, data, piece=piece, nt=nt)
+            _roundtrip(emul, data, piece=piece, nt=nt, model=0)
+            _roundtrip(emul, data, piece=piece, nt=nt, row=48, pixel=3)
 
 
 def test_every_run_length_at_every_alignment(emul):

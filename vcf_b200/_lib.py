@@ -85,6 +85,8 @@ def lib():
     L.vcfb_deflate_workspace.restype = sz
     L.vcfb_deflate_dev.argtypes = [vp, sz, vp, sz, vp, vp, sz, vp]
     L.vcfb_deflate_dev.restype = i
+    L.vcfb_deflate_rows_dev.argtypes = [vp, sz, sz, i, vp, sz, vp, vp, sz, vp]
+    L.vcfb_deflate_rows_dev.restype = i
     L.vcfb_crc32_dev.argtypes = [vp, sz, vp, vp]
     L.vcfb_crc32_dev.restype = i
     L.vcfb_adler32_dev.argtypes = [vp, sz, vp, vp, vp]

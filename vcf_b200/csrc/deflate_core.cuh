@@ -2,10 +2,12 @@
 //
 // The reference hands the uint8 index planes of the transform path to zlib: np.savez_compressed
 // in src/z_lib.py:19-23, tifffile's zlib codec in src/TIFF.py:23-31.  The planes are long runs of
-// the bias value 128 with sparse, strongly skewed literals, so a run-length parse (matches of
-// distance 1 only, zlib's Z_RLE strategy) under a dynamic Huffman code is within a few per cent of
-// zlib's default parse -- and, unlike hash-chain matching, it is a pure function of each byte's
-// neighbours, so every thread can parse its own piece of the input.
+// the bias value 128 with sparse, strongly skewed literals.  The parse is greedy over a FIXED set of
+// candidate distances (MatchParams): distance 1 (runs -- zlib's Z_RLE strategy) and, when the caller
+// names the row length of the planes, the bytes of the row above (row - 1, row, row + 1: where
+// zlib's hash chains find most of their matches in a subband plane).  Whether a position starts a
+// match is then a function of a bounded neighbourhood of the input alone -- no hash table, no
+// state carried along the stream -- so every thread can parse its own piece.
 //
 // One *segment* (one CTA) becomes one dynamic-Huffman block that ends on a byte boundary (an
 // empty stored block, like zlib's Z_SYNC_FLUSH), so the streams of the segments concatenate.
@@ -36,6 +38,9 @@ constexpr int MAX_CL_BITS = 7;
 constexpr int MAX_MATCH = 258;
 constexpr int MIN_MATCH = 3;
 constexpr int STORED_MAX = 65535;
+constexpr int NDIST = 30;      // distance alphabet
+constexpr int MAX_CAND = 8;    // candidate distances of the parse
+constexpr int FAR_MIN = 4;     // shortest match at a distance other than 1 (found by comparing eight bytes at once)
 
 // ---- match lengths ------------------------------------------------------------------------------
 
@@ -51,60 +56,330 @@ DFL_HD void length_symbol(int L, int* sym, int* ebits, int* eval) {
   *eval = l & ((1 << e) - 1);
 }
 
-// ---- run-length parse ---------------------------------------------------------------------------
+// ---- distances ------------------------------------------------------------------------------------
 
-// Tokens of the piece [s, e) of src[0, n): a byte equal to its predecessor starts a match of
-// distance 1 when at least MIN_MATCH bytes repeat (the predecessor may lie in the previous piece
-// or segment: the decoder has produced it by then).  V::lit(byte) / V::match(length).
-// src must be 8-byte aligned.  The input is read as aligned 64-bit words kept in a register (one
-// load per 8 bytes: the pieces of a warp's threads lie `piece` bytes apart, so every load costs one
-// L1 wavefront per thread -- measured neutral against byte loads); bytes past n are
-// never touched.
+// RFC 1951 3.2.5: distance d in [1, 32768] -> symbol 0..29, number of extra bits, extra value
+DFL_HD void distance_symbol(int d, int* sym, int* ebits, int* eval) {
+  const int x = d - 1;
+  if (x < 4) { *sym = x; *ebits = 0; *eval = 0; return; }
+  int e = -1;                      // floor(log2(x)) - 1
+  for (int t = x >> 1; t; t >>= 1) ++e;
+  *sym = 2 * (e + 1) + ((x >> e) & 1);
+  *ebits = e;
+  *eval = x & ((1 << e) - 1);
+}
+
+// The candidate distances of the parse and what each costs.  dist[0] is always 1.
+struct MatchParams {
+  int nd;
+  int good;                     // a run at least this long is taken without looking at the other candidates
+  int margin8;                  // estimated saving (1/8 bit) a match at another distance must exceed
+  int patience;                 // positions in a row without such a match after which a piece stops looking for one
+  int dist[MAX_CAND];
+  uint8_t dsym[MAX_CAND], debits[MAX_CAND];
+  uint16_t deval[MAX_CAND];
+  uint8_t minlen[MAX_CAND];     // shortest match at this distance
+  uint8_t dcost8[MAX_CAND];     // estimated size of the distance code + its extra bits, in 1/8 bit
+};
+
+inline void match_params_add(MatchParams& P, int d, int minlen) {
+  if (d < 1 || d > 32768 || P.nd >= MAX_CAND) return;
+  for (int i = 0; i < P.nd; ++i) if (P.dist[i] == d) return;
+  int s, eb, ev;
+  distance_symbol(d, &s, &eb, &ev);
+  const int i = P.nd++;
+  P.dist[i] = d; P.dsym[i] = uint8_t(s); P.debits[i] = uint8_t(eb); P.deval[i] = uint16_t(ev);
+  P.minlen[i] = uint8_t(minlen);
+  P.dcost8[i] = uint8_t(d == 1 ? 12 : 8 * (3 + eb));     // the run distance gets the shortest code; the others about 3 bits
+}
+
+// row = 0: runs only (the parse of zlib's Z_RLE).  Otherwise the input is an array of rows of `row`
+// bytes whose samples lie `pixel` bytes apart (3 for the H x W x 3 index image the reference hands
+// to its entropy stage): the previous sample of the same channel and the samples above it are
+// candidates too.
+inline MatchParams make_match_params(long long row, int pixel) {
+  MatchParams P;
+  P.nd = 0;
+  P.good = 64;
+  P.margin8 = 0;
+  P.patience = 64;
+  for (int i = 0; i < MAX_CAND; ++i) { P.dist[i] = 0; P.dsym[i] = 0; P.debits[i] = 0; P.deval[i] = 0; P.minlen[i] = 0; P.dcost8[i] = 0; }
+  match_params_add(P, 1, MIN_MATCH);
+  if (pixel < 1) pixel = 1;
+  if (row > 0) {
+    if (pixel > 1) match_params_add(P, pixel, FAR_MIN);
+    if (row > 2 * pixel && row + pixel <= 32768) {
+      match_params_add(P, int(row), FAR_MIN);
+      match_params_add(P, int(row) - pixel, FAR_MIN);
+      match_params_add(P, int(row) + pixel, FAR_MIN);
+    }
+  }
+  return P;
+}
+
 #if defined(__CUDA_ARCH__)
 #define DFL_CTZ64(x) (__ffsll((long long)(x)) - 1)
 #else
 #define DFL_CTZ64(x) __builtin_ctzll(x)
 #endif
 
+// src must be 8-byte aligned.  The input is read as aligned 64-bit words; bytes past n are never touched.
+// CHK = false: the caller knows that base + 8 <= n (every piece but the last few of the input), which
+// takes a 64-bit comparison and a branch off every load -- a sixth of the parse's instructions.
+template <bool CHK = true>
 DFL_HD uint64_t load_word(const uint8_t* src, long long n, long long base) {
-  if (base + 8 <= n) return *reinterpret_cast<const uint64_t*>(src + base);
+  if (!CHK || base + 8 <= n) return *reinterpret_cast<const uint64_t*>(src + base);
   uint64_t x = 0;
   for (int k = 0; base + k < n; ++k) x |= uint64_t(src[base + k]) << (8 * k);
   return x;
 }
 
-template <class V>
-DFL_HD void parse_piece(const uint8_t* src, long long n, long long s, long long e, V& v) {
+// ---- cost model of the parse --------------------------------------------------------------------
+//
+// A greedy parse that takes every match it finds is larger than the run-length parse on dense planes:
+// three literals of a skewed alphabet take fewer bits than a match with a 7-bit distance.  So the
+// segment is sampled first (every fourth 64-bit word): bytes that differ from their predecessor
+// stand for the literals, those followed by a copy of themselves for the starts of runs; the
+// estimated code lengths (in 1/8 bit, integer arithmetic only -- the host emulation gives the same
+// tokens) decide whether a match is worth its bits.
+
+constexpr int SAMPLE_EVERY = 4;
+
+DFL_HD int ilog2_u32(uint32_t x) {           // x >= 1
+#if defined(__CUDA_ARCH__)
+  return 31 - __clz(int(x));
+#else
+  return 31 - __builtin_clz(x);
+#endif
+}
+
+// 8 * log2(num / den), num >= den >= 1, num < 2^23
+DFL_HD int cost8_ratio(uint32_t num, uint32_t den) {
+  const uint32_t r = (num << 8) / den;        // >= 256
+  const int e = ilog2_u32(r);
+  const int f = int((r >> (e - 3)) & 7);      // the three bits below the leading one
+  const int frac = (0x76654310 >> (4 * f)) & 15;   // 8 * log2(1 + f / 8), rounded: 0 1 3 4 5 6 6 7
+  return 8 * (e - 8) + frac;
+}
+
+struct CostModel {
+  uint8_t lit8[256];    // estimated bits * 8 of a literal
+  int len8;             // of a length symbol (without extra bits)
+};
+
+// Counts of one sampled word w at byte position pos: wp / wn are the words before and after it
+// (zero where there is none).  A byte belongs to a run when three consecutive bytes around it equal
+// their predecessors; every other byte counts as a literal, every start of a run as a match.
+template <class Add>
+DFL_HD void sample_word(uint64_t wp, uint64_t w, uint64_t wn, long long pos, long long n, Add& add) {
+  uint32_t eq = 0;                                   // bit i: byte i of (wp, w, wn) equals byte i - 1, i in [1, 24)
+  int prev = int(wp & 0xff);
+  for (int i = 1; i < 24; ++i) {
+    const uint64_t x = i < 8 ? wp : i < 16 ? w : wn;
+    const int b = int((x >> (8 * (i & 7))) & 0xff);
+    const long long at = pos - 8 + i;
+    if (b == prev && at >= 1 && at < n) eq |= 1u << i;
+    prev = b;
+  }
+  const uint32_t t = eq & (eq >> 1) & (eq >> 2);     // bit i: bytes i, i + 1, i + 2 all equal their predecessors
+  const uint32_t inrun = t | (t << 1) | (t << 2);
+  for (int i = 8; i < 16; ++i) {
+    if (pos - 8 + i >= n) break;
+    if (!((inrun >> i) & 1)) add.lit(int((w >> (8 * (i & 7))) & 0xff));
+    else if (!((inrun >> (i - 1)) & 1)) add.run();
+  }
+}
+
+// the sampled words of the segment [s0, s0 + nseg) that thread tid of NT looks at
+template <class Add>
+DFL_HD void sample_segment(const uint8_t* src, long long n, long long s0, long long nseg, int tid, int NT, Add& add) {
+  const long long first = ((s0 + 7) / 8 + SAMPLE_EVERY - 1) / SAMPLE_EVERY * SAMPLE_EVERY;
+  for (long long aw = first + (long long)SAMPLE_EVERY * tid; aw * 8 < s0 + nseg; aw += (long long)SAMPLE_EVERY * NT) {
+    const long long pos = aw * 8;
+    sample_word(pos >= 8 ? load_word(src, n, pos - 8) : 0, load_word(src, n, pos), pos + 8 < n ? load_word(src, n, pos + 8) : 0,
+                pos, n, add);
+  }
+}
+
+// entry b of the cost table from the sampled counts (cnt[256] literals, nlit their sum, nrun run starts)
+DFL_HD uint8_t model_lit8(const uint32_t* cnt, uint32_t nlit, uint32_t nrun, int b) {
+  const uint32_t ntok = nlit + nrun + 1;
+  const uint32_t c = cnt[b];
+  int v = c ? cost8_ratio(ntok, c) : cost8_ratio(2 * ntok, 1);
+  if (v < 8) v = 8;
+  if (v > 120) v = 120;
+  return uint8_t(v);
+}
+
+DFL_HD int model_len8(uint32_t nlit, uint32_t nrun) {
+  const uint32_t ntok = nlit + nrun + 1;
+  int v = cost8_ratio(ntok, nrun ? nrun : 1) + 16;     // the matches spread over several length symbols
+  if (v < 16) v = 16;
+  if (v > 96) v = 96;
+  return v;
+}
+
+
+// ---- parse ----------------------------------------------------------------------------------------
+
+// the eight bytes at an arbitrary position (zeros past n); CHK = false: pos + 16 <= n
+template <bool CHK = true>
+DFL_HD uint64_t load_u64_at(const uint8_t* src, long long n, long long pos) {
+  const long long base = pos & ~7ll;
+  const int off = int(pos & 7);
+  const uint64_t w0 = load_word<CHK>(src, n, base);
+  if (!off) return w0;
+  const uint64_t w1 = (!CHK || base + 8 < n) ? load_word<CHK>(src, n, base + 8) : 0;
+  return (w0 >> (8 * off)) | (w1 << (64 - 8 * off));
+}
+
+// number of bytes (at most lim) for which src[p + k] == src[p - d + k]; CHK = false: p + lim + 16 <= n
+template <bool CHK = true>
+DFL_HD int match_length(const uint8_t* src, long long n, long long p, int d, int lim) {
+  int L = 0;
+  while (L < lim) {
+    const uint64_t x = load_u64_at<CHK>(src, n, p + L) ^ load_u64_at<CHK>(src, n, p + L - d);
+    if (x) { L += DFL_CTZ64(x) >> 3; break; }
+    L += 8;
+  }
+  return L < lim ? L : lim;
+}
+
+// estimated size (1/8 bit) of a run of r bytes equal to their predecessor: literals, or a match of distance 1
+DFL_HD int run_cost8(int r, int lit8, const MatchParams& P, const CostModel& M) {
+  const int as_lit = r * lit8;
+  if (r < MIN_MATCH) return as_lit;
+  int sym, eb, ev;
+  length_symbol(r, &sym, &eb, &ev);
+  const int as_match = M.len8 + 8 * eb + int(P.dcost8[0]);
+  return as_match < as_lit ? as_match : as_lit;
+}
+
+// estimated size of src[p, p + L) under the run-length parse (prev = the byte before p): what a
+// match at another distance has to beat.  Eight bytes at a time where they continue a run; gives
+// up (returning what it has) once the estimate is above `enough`.
+template <bool CHK = true>
+DFL_HD int span_cost8(const uint8_t* src, long long n, long long p, int L, int prev, const MatchParams& P,
+                      const CostModel& M, int enough) {
+  int cost = 0, run = 0, pb = prev;
+  for (int k = 0; k < L;) {
+    const uint64_t w = load_u64_at<CHK>(src, n, p + k);
+    const int nb = L - k < 8 ? L - k : 8;
+    if (nb == 8 && pb >= 0 && w == 0x0101010101010101ull * uint64_t(pb)) { run += 8; k += 8; continue; }
+    for (int i = 0; i < nb; ++i) {
+      const int b = int((w >> (8 * i)) & 0xff);
+      if (b == pb) { ++run; continue; }
+      if (run) { cost += run_cost8(run, int(M.lit8[pb]), P, M); run = 0; }
+      cost += M.lit8[b];
+      pb = b;
+    }
+    k += nb;
+    if (cost > enough) return cost;
+  }
+  if (run) cost += run_cost8(run, int(M.lit8[pb]), P, M);
+  return cost;
+}
+
+// Tokens of the piece [s, e) of src[0, n), greedy.  At every position: the run (distance 1) when it
+// is cheaper than its bytes as literals; the longest match over the other candidate distances when
+// it is estimated to take fewer bits than the run-length parse of the bytes it covers; else a
+// literal.  A match never leaves the piece; its source may lie in an earlier piece or segment (the
+// decoder has produced it by then).  V::lit(byte) / V::match(length, candidate).  M == nullptr:
+// every run of MIN_MATCH bytes or more is a match (the plain run-length parse; one candidate only).
+// CHK = false: e + 16 <= n, no load looks at n.
+template <bool CHK, class V>
+DFL_HD void parse_piece_impl(const uint8_t* src, long long n, long long s, long long e, const MatchParams& P,
+                        const CostModel* M, V& v) {
   long long p = s;
   int prev = p > 0 ? int(src[p - 1]) : -1;
   long long wbase = -8;
   uint64_t w = 0;
+  bool far_on = M && P.nd > 1;
+  int fails = 0;
   while (p < e) {
     const long long base = p & ~7ll;
-    if (base != wbase) { w = load_word(src, n, base); wbase = base; }
+    if (base != wbase) { w = load_word<CHK>(src, n, base); wbase = base; }
     const int b = int((w >> (8 * int(p & 7))) & 0xff);
+    const long long rem = e - p;
+    const int lim = rem < MAX_MATCH ? int(rem) : MAX_MATCH;
+    int best = 0, bc = 0;
     if (b == prev) {
-      const long long rem = e - p;
-      const int lim = rem < MAX_MATCH ? int(rem) : MAX_MATCH;
       const uint64_t splat = 0x0101010101010101ull * uint64_t(prev);
       int L = 0;
+      long long rb = wbase;
+      uint64_t rw = w;
       for (;;) {
         const int off = int((p + L) & 7);
-        const uint64_t x = (w ^ splat) >> (8 * off);
+        const uint64_t x = (rw ^ splat) >> (8 * off);
         const int avail = 8 - off;
         const int z = x ? (DFL_CTZ64(x) >> 3) : avail;    // a differing byte lies inside the `avail` valid ones
         L += z;
         if (z < avail || L >= lim) break;
-        wbase += 8;
-        w = load_word(src, n, wbase);
+        rb += 8;
+        rw = load_word<CHK>(src, n, rb);
       }
       if (L > lim) L = lim;
-      if (L >= MIN_MATCH) { v.match(L); p += L; continue; }
+      if (L >= MIN_MATCH) {
+        if (!M) best = L;
+        else {
+          int sym, eb, ev;
+          length_symbol(L, &sym, &eb, &ev);
+          if (L * int(M->lit8[b]) > M->len8 + 8 * eb + int(P.dcost8[0])) best = L;
+        }
+      }
+    }
+    if (far_on && best < lim && best < P.good && lim >= FAR_MIN) {
+      const uint64_t win = load_u64_at<CHK>(src, n, p);
+      int fl = 0, fc = 0;                                  // the longest match at another distance
+      for (int c = 1; c < P.nd; ++c) {
+        const int d = P.dist[c];
+        if (p < d) continue;
+        const uint64_t x = win ^ load_u64_at<CHK>(src, n, p - d);
+        int L = x ? (DFL_CTZ64(x) >> 3) : 8;
+        if (L < FAR_MIN) continue;
+        if (L == 8 && lim > 8) L += match_length<CHK>(src, n, p + 8, d, lim - 8);
+        if (L > lim) L = lim;
+        if (L > fl) { fl = L; fc = c; }
+      }
+      bool taken = false;
+      if (fl > best) {
+        int sym, eb, ev;
+        length_symbol(fl, &sym, &eb, &ev);
+        const int cost = M->len8 + 8 * eb + int(P.dcost8[fc]) + P.margin8;
+        if (span_cost8<CHK>(src, n, p, fl, prev, P, *M, cost) > cost) { best = fl; bc = fc; taken = true; }
+      }
+      if (taken) fails = 0;
+      else if (++fails >= P.patience) far_on = false;      // dense content: nothing to find above, stop looking
+    }
+    if (best) {
+      v.match(best, bc);
+      p += best;
+      if (bc) prev = int(src[p - 1]);
+      continue;
     }
     v.lit(b);
     prev = b;
     ++p;
   }
+}
+
+template <class V>
+DFL_HD void parse_piece(const uint8_t* src, long long n, long long s, long long e, const MatchParams& P,
+                        const CostModel* M, V& v) {
+  if (e + 16 <= n) parse_piece_impl<false>(src, n, s, e, P, M, v);
+  else parse_piece_impl<true>(src, n, s, e, P, M, v);
+}
+
+// A token in 16 bits: a literal is its byte; a match is 256 + (length - 3) in bits 0..8 and the
+// candidate in bits 9..11.  The kernel parses once, keeps the tokens and walks them twice more.
+DFL_HD uint16_t token_lit(int b) { return uint16_t(b); }
+DFL_HD uint16_t token_match(int L, int c) { return uint16_t(256 + (L - MIN_MATCH) + (c << 9)); }
+
+template <class V>
+DFL_HD void visit_token(uint16_t t, V& v) {
+  const int x = t & 511;
+  if (x < 256) v.lit(x);
+  else v.match(x - 256 + MIN_MATCH, t >> 9);
 }
 
 // ---- bit output ---------------------------------------------------------------------------------
@@ -148,6 +423,8 @@ struct BitWriter {
 struct Codes {
   uint16_t code[NLIT];   // bit-reversed, ready for LSB-first output
   uint8_t len[NLIT];
+  uint16_t dcode[NDIST + 2];
+  uint8_t dlen[NDIST + 2];
 };
 
 #if defined(__CUDA_ARCH__)
@@ -158,44 +435,65 @@ struct Codes {
 
 struct CountVisitor {      // symbol frequencies; equal consecutive symbols (runs of 258-byte matches) are added at once
   uint32_t* hist;
+  uint32_t* dhist;
+  const MatchParams* P;
   int cur;
-  uint32_t cnt;
-  DFL_HD void init(uint32_t* h) { hist = h; cur = 0; cnt = 0; }
-  DFL_HD void flush() { if (cnt) { DFL_ATOMIC_ADD(hist + cur, cnt); } cnt = 0; }
+  uint32_t cnt, d0;
+  DFL_HD void init(uint32_t* h, uint32_t* dh, const MatchParams* p) { hist = h; dhist = dh; P = p; cur = 0; cnt = 0; d0 = 0; }
+  DFL_HD void flush() {
+    if (cnt) { DFL_ATOMIC_ADD(hist + cur, cnt); }
+    if (d0) { DFL_ATOMIC_ADD(dhist + P->dsym[0], d0); }
+    cnt = 0; d0 = 0;
+  }
   DFL_HD void add(int sym) {
-    if (sym != cur) { flush(); cur = sym; }
+    if (sym != cur) { if (cnt) { DFL_ATOMIC_ADD(hist + cur, cnt); } cnt = 0; cur = sym; }
     ++cnt;
   }
   DFL_HD void lit(int b) { add(b); }
-  DFL_HD void match(int L) {
+  DFL_HD void match(int L, int c) {
     int sym, eb, ev;
     length_symbol(L, &sym, &eb, &ev);
     add(sym);
+    if (c == 0) ++d0;
+    else DFL_ATOMIC_ADD(dhist + P->dsym[c], 1u);
   }
 };
 
-struct SizeVisitor {       // bits the tokens take under `len`
-  const uint8_t* len;
+struct SizeVisitor {       // bits the tokens take under the codes
+  const Codes* c;
+  const MatchParams* P;
   unsigned bits;
-  DFL_HD void lit(int b) { bits += len[b]; }
-  DFL_HD void match(int L) {
+  DFL_HD void lit(int b) { bits += c->len[b]; }
+  DFL_HD void match(int L, int k) {
     int sym, eb, ev;
     length_symbol(L, &sym, &eb, &ev);
-    bits += len[sym] + eb + 1;      // + the 1-bit distance code
+    bits += c->len[sym] + eb + c->dlen[P->dsym[k]] + P->debits[k];
   }
 };
 
 struct EmitVisitor {
   const Codes* c;
+  const MatchParams* P;
   BitWriter* bw;
   DFL_HD void lit(int b) { bw->put(c->code[b], c->len[b]); }
-  DFL_HD void match(int L) {
+  DFL_HD void match(int L, int k) {
     int sym, eb, ev;
     length_symbol(L, &sym, &eb, &ev);
     const int n = c->len[sym];
-    // length code, extra bits, distance symbol 0 = code "0" of length 1
-    bw->put(uint32_t(c->code[sym]) | (uint32_t(ev) << n), n + eb + 1);
+    bw->put(uint32_t(c->code[sym]) | (uint32_t(ev) << n), n + eb);               // <= 15 + 5 bits
+    const int ds = P->dsym[k], dn = c->dlen[ds];
+    bw->put(uint32_t(c->dcode[ds]) | (uint32_t(P->deval[k]) << dn), dn + P->debits[k]);   // <= 15 + 13 bits
   }
+};
+
+// parse visitor of the kernel's first pass: keeps the token (strided store) and counts it
+template <class Store>
+struct TokenVisitor {
+  Store st;
+  CountVisitor cv;
+  int n;
+  DFL_HD void lit(int b) { st(n++, token_lit(b)); cv.lit(b); }
+  DFL_HD void match(int L, int c) { st(n++, token_match(L, c)); cv.match(L, c); }
 };
 
 // ---- Huffman code construction ------------------------------------------------------------------
@@ -402,10 +700,11 @@ DFL_HD void par_codes(const BuildScratch& S, int n, const uint8_t* len, uint16_t
 // ---- block header -------------------------------------------------------------------------------
 
 struct Header {
-  uint8_t tok_sym[NLIT + 2 + 8];   // code-length tokens of the concatenated length arrays
-  uint8_t tok_ext[NLIT + 2 + 8];
+  uint8_t tok_sym[NLIT + NDIST + 8];   // code-length tokens of the concatenated length arrays
+  uint8_t tok_ext[NLIT + NDIST + 8];
   int ntok;
   int hlit;                         // literal/length codes sent (>= 257)
+  int hdist;                        // distance codes sent (>= 2 here)
   int hclen;                        // code-length codes sent (>= 4)
   uint32_t clfreq[NCL];
   uint16_t clcode[NCL];
@@ -421,20 +720,22 @@ DFL_HD void header_tok(Header& h, int sym, int ext) {
 }
 
 // Run-length tokens (symbols 16/17/18 of RFC 1951 3.2.7) for the lengths of the literal/length
-// code followed by the two distance codes of length 1 (one distance is ever used; like zlib we
-// send two so the distance code is complete).
-DFL_HD void header_tokens(const uint8_t* litlen, Header& h) {
+// code followed by those of the distance code.
+DFL_HD void header_tokens(const uint8_t* litlen, const uint8_t* dlen, Header& h) {
   int hlit = NLIT;
   while (hlit > 257 && litlen[hlit - 1] == 0) --hlit;
   h.hlit = hlit;
+  int hdist = NDIST;
+  while (hdist > 1 && dlen[hdist - 1] == 0) --hdist;
+  h.hdist = hdist;
   h.ntok = 0;
   for (int i = 0; i < NCL; ++i) h.clfreq[i] = 0;
-  const int total = hlit + 2;
+  const int total = hlit + hdist;
   int i = 0;
   while (i < total) {
-    const int v = i < hlit ? litlen[i] : 1;
+    const int v = i < hlit ? litlen[i] : dlen[i - hlit];
     int r = 1;
-    while (i + r < total && (i + r < hlit ? litlen[i + r] : 1) == v) ++r;
+    while (i + r < total && (i + r < hlit ? litlen[i + r] : dlen[i + r - hlit]) == v) ++r;
     i += r;
     if (v == 0) {
       while (r >= 11) { const int c = r < 138 ? r : 138; header_tok(h, 18, c - 11); r -= c; }
@@ -471,7 +772,7 @@ DFL_HD void header_emit(const Header& h, BitWriter& bw) {
   bw.put(0, 1);                 // BFINAL = 0: the stream is closed by the caller
   bw.put(2, 2);                 // BTYPE = 10, dynamic Huffman
   bw.put(uint32_t(h.hlit - 257), 5);
-  bw.put(1, 5);                 // HDIST = 2 codes
+  bw.put(uint32_t(h.hdist - 1), 5);
   bw.put(uint32_t(h.hclen - 4), 4);
   for (int i = 0; i < h.hclen; ++i) bw.put(h.cllen[cl_order(i)], 3);
   for (int t = 0; t < h.ntok; ++t) {
@@ -505,9 +806,22 @@ DFL_HD void stored_copy(const uint8_t* seg, long long n, long long s, long long 
 
 // ---- the serial part of a segment (one thread) ------------------------------------------------------
 
+// The distance code of a segment from the frequencies of its distance symbols (one thread; at most
+// MAX_CAND symbols are in use).  A complete code needs two symbols: like zlib, unused ones are
+// sent to fill up.  dhist is changed.
+DFL_HD void distance_code(uint32_t* dhist, BuildScratch& S, Codes& c) {
+  int used = 0;
+  for (int i = 0; i < NDIST; ++i) used += dhist[i] != 0;
+  for (int i = 0; used < 2 && i < NDIST; ++i)
+    if (dhist[i] == 0) { dhist[i] = 1; ++used; }
+  for (int i = 0; i < NDIST; ++i)
+    if (dhist[i]) S.sorted[rank_of(dhist, NDIST, i)] = uint16_t(i);
+  build_code(dhist, NDIST, used, MAX_LIT_BITS, S, c.dcode, c.dlen);
+}
+
 // hist: frequencies of the literal/length symbols of the segment (EOB counted once, so at least
 // two symbols are used); S.sorted: the used symbols by ascending (frequency, symbol).  Builds the literal/length
-// code, the header tokens and the code-length code.
+// code, the header tokens and the code-length code; c.dlen is the finished distance code.
 DFL_HD void segment_header(BuildScratch& S, const Codes& c, Header& h);
 
 DFL_HD void segment_build(const uint32_t* hist, BuildScratch& S, Codes& c, Header& h) {
@@ -517,9 +831,9 @@ DFL_HD void segment_build(const uint32_t* hist, BuildScratch& S, Codes& c, Heade
   segment_header(S, c, h);
 }
 
-// the block header for the finished literal/length code (one thread)
+// the block header for the finished codes (one thread)
 DFL_HD void segment_header(BuildScratch& S, const Codes& c, Header& h) {
-  header_tokens(c.len, h);
+  header_tokens(c.len, c.dlen, h);
   int used = 0;
   for (int i = 0; i < NCL; ++i) used += h.clfreq[i] != 0;
   for (int i = 0; used < 2 && i < NCL; ++i)            // a complete code needs two symbols

@@ -6,12 +6,15 @@
 // tifffile read it.  It is not byte-identical with zlib's output (no two deflate encoders are);
 // the drop-in property is "the reference's decoder returns the same bytes".
 //
-//   deflate_segments_kernel  one CTA per segment of NT pieces.  Phase 1: every thread parses its
-//       piece (run-length parse, deflate_core.cuh) into a shared histogram.  Phase 2: Huffman
-//       code in CTA-parallel steps (rank sort, serial two-queue merge, lengths, canonical codes), block header by thread 0.  Phase 3:
-//       every thread sizes its piece under the code; exclusive scan -> bit offsets; the segment
-//       falls back to stored blocks when those are smaller.  Phase 4: the CTA zeroes exactly the
-//       bytes the block takes, every thread writes its tokens at its bit offset (first and last
+//   deflate_segments_kernel  one CTA per segment of NT pieces.  Phase 0: the CTA samples the segment
+//       (every fourth word) for the cost model of the parse.  Phase 1: every thread parses its
+//       piece (greedy over the candidate distances, deflate_core.cuh), keeps the tokens (16 bits
+//       each, token j of all threads side by side) and counts them into shared histograms.  Phase 2:
+//       Huffman codes -- literal/length in CTA-parallel steps (rank sort, serial two-queue merge,
+//       lengths, canonical codes), distances by one thread beside it, block header by thread 0.
+//       Phase 3: every thread sizes its tokens under the codes; exclusive scan -> bit offsets; the
+//       segment falls back to stored blocks when those are smaller.  Phase 4: the CTA zeroes exactly
+//       the bytes the block takes, every thread writes its tokens at its bit offset (first and last
 //       word with atomicOr, the rest with plain stores).
 //   deflate_scan_kernel      exclusive scan of the segment sizes, total size, closing block.
 //   deflate_gather_kernel    copies every segment's bytes to its place in the output stream.
@@ -31,7 +34,7 @@ struct Plan {
   long long seg_bytes;    // bytes per segment = NT * piece
   long long nseg;
   long long stride;       // bytes of scratch per segment
-  long long sizes_off, offs_off, regions_off, total;   // workspace layout
+  long long sizes_off, offs_off, regions_off, tokens_off, total;   // workspace layout
   long long bound;        // largest possible stream
 };
 
@@ -52,25 +55,49 @@ Plan make_plan(unsigned long long n) {
   p.sizes_off = 0;
   p.offs_off = (p.nseg * 4 + 15) / 16 * 16;
   p.regions_off = p.offs_off + (p.nseg * 8 + 15) / 16 * 16;
-  p.total = p.regions_off + p.nseg * p.stride + 16;
+  p.tokens_off = p.regions_off + p.nseg * p.stride;            // 16 bits per input byte at most
+  p.total = p.tokens_off + p.nseg * p.seg_bytes * 2 + 16;
   p.bound = (long long)n + 5 * p.nseg * ((p.seg_bytes + dfl::STORED_MAX - 1) / dfl::STORED_MAX) + 2;
   return p;
 }
 
 struct SegShared {
   uint32_t hist[288];
+  uint32_t dhist[32];
+  uint32_t scnt[256];     // sampled literals
+  uint32_t stot[2];       // their number, the number of sampled run starts
+  dfl::MatchParams mp;
+  dfl::CostModel cm;
   dfl::Codes codes;
   dfl::Header hdr;
   dfl::BuildScratch scratch;
+  dfl::BuildScratch dscratch;
   uint32_t off[NT];
   uint32_t wsum[NT / 32];
   long long total_bytes;
   int stored;
 };
 
-__global__ void __launch_bounds__(NT, 3)
-deflate_segments_kernel(const uint8_t* __restrict__ src, long long n, int piece, uint8_t* __restrict__ regions,
-                        long long stride, uint32_t* __restrict__ seg_size) {
+struct SampleAdd {
+  uint32_t* cnt;
+  uint32_t* tot;
+  __device__ void lit(int b) { atomicAdd(cnt + b, 1u); atomicAdd(tot, 1u); }
+  __device__ void run() { atomicAdd(tot + 1, 1u); }
+};
+
+struct TokenStore {        // token j of this thread; the tokens of a segment are laid out j-major
+  uint16_t* base;
+  __device__ void operator()(int j, uint16_t t) const { base[(long long)j * NT] = t; }
+};
+
+#ifndef DFL_MINB
+#define DFL_MINB 3
+#endif
+
+__global__ void __launch_bounds__(NT, DFL_MINB)
+deflate_segments_kernel(const uint8_t* __restrict__ src, long long n, int piece, dfl::MatchParams mp,
+                        uint8_t* __restrict__ regions, long long stride, uint16_t* __restrict__ tokens,
+                        uint32_t* __restrict__ seg_size) {
   __shared__ SegShared sh;
   const int tid = threadIdx.x;
   const long long seg = blockIdx.x;
@@ -81,20 +108,40 @@ deflate_segments_kernel(const uint8_t* __restrict__ src, long long n, int piece,
   const long long e = min(n, s + piece);
   uint8_t* out = regions + seg * stride;
 
+  uint16_t* tok = tokens + seg * seg_bytes + tid;
+
   for (int i = tid; i < 288; i += NT) sh.hist[i] = 0;
+  if (tid < 256) sh.scnt[tid] = 0;
+  if (tid < 32) sh.dhist[tid] = 0;
   if (tid <= dfl::MAX_LIT_BITS) sh.scratch.cnt[tid] = 0;
-  if (tid == 32) { sh.scratch.m = 0; sh.scratch.hi = 0; }
+  if (tid == 32) { sh.scratch.m = 0; sh.scratch.hi = 0; sh.stot[0] = 0; sh.stot[1] = 0; }
+  if (tid == 64) sh.mp = mp;
   __syncthreads();
   if (tid == 0) sh.hist[dfl::EOB] = 1;
 
-  // phase 1: symbol frequencies
+  // phase 0: cost model of the parse from a sample of the segment
   {
-    dfl::CountVisitor cv;
-    cv.init(sh.hist);
-    dfl::parse_piece(src, n, s, e, cv);
-    cv.flush();
+    SampleAdd add{sh.scnt, sh.stot};
+    dfl::sample_segment(src, n, s0, nseg, tid, NT, add);
   }
   __syncthreads();
+  if (tid < 256) sh.cm.lit8[tid] = dfl::model_lit8(sh.scnt, sh.stot[0], sh.stot[1], tid);
+  if (tid == 256) sh.cm.len8 = dfl::model_len8(sh.stot[0], sh.stot[1]);
+  __syncthreads();
+
+  // phase 1: parse; tokens and their frequencies
+  int ntok;
+  {
+    dfl::TokenVisitor<TokenStore> tv;
+    tv.st.base = tok;
+    tv.n = 0;
+    tv.cv.init(sh.hist, sh.dhist, &sh.mp);
+    dfl::parse_piece(src, n, s, e, sh.mp, &sh.cm, tv);
+    tv.cv.flush();
+    ntok = tv.n;
+  }
+  __syncthreads();
+  if (tid == 32) dfl::distance_code(sh.dhist, sh.dscratch, sh.codes);     // a few symbols: one thread, beside the rank sort
 
   // phase 2: code construction
   //  (the steps of deflate_core.cuh: only the two-queue merge, the Kraft fix and the header are serial)
@@ -117,9 +164,10 @@ deflate_segments_kernel(const uint8_t* __restrict__ src, long long n, int piece,
   // phase 3: sizes and bit offsets
   {
     dfl::SizeVisitor sv;
-    sv.len = sh.codes.len;
+    sv.c = &sh.codes;
+    sv.P = &sh.mp;
     sv.bits = 0;
-    dfl::parse_piece(src, n, s, e, sv);
+    for (int j = 0; j < ntok; ++j) dfl::visit_token(tok[(long long)j * NT], sv);
     sh.off[tid] = sv.bits;
   }
   __syncthreads();
@@ -175,8 +223,9 @@ deflate_segments_kernel(const uint8_t* __restrict__ src, long long n, int piece,
     if (tid == 0) dfl::header_emit(sh.hdr, bw);
     dfl::EmitVisitor ev;
     ev.c = &sh.codes;
+    ev.P = &sh.mp;
     ev.bw = &bw;
-    dfl::parse_piece(src, n, s, e, ev);
+    for (int j = 0; j < ntok; ++j) dfl::visit_token(tok[(long long)j * NT], ev);
     if (tid == NT - 1) dfl::segment_close(sh.codes, bw);
     bw.finish();
   }
@@ -320,6 +369,12 @@ size_t vcfb_deflate_workspace(size_t n_bytes) { return size_t(make_plan(n_bytes)
 
 int vcfb_deflate_dev(const uint8_t* src, size_t n_bytes, uint8_t* dst, size_t dst_capacity,
                      uint64_t* out_bytes, void* workspace, size_t workspace_bytes, void* cuda_stream) {
+  return vcfb_deflate_rows_dev(src, n_bytes, 0, 1, dst, dst_capacity, out_bytes, workspace, workspace_bytes, cuda_stream);
+}
+
+int vcfb_deflate_rows_dev(const uint8_t* src, size_t n_bytes, size_t row_bytes, int sample_bytes, uint8_t* dst,
+                          size_t dst_capacity, uint64_t* out_bytes, void* workspace, size_t workspace_bytes,
+                          void* cuda_stream) {
   if (!dst || !out_bytes) { set_error("output pointer is NULL"); return VCFB_E_ARG; }
   if (n_bytes && !src) { set_error("input pointer is NULL"); return VCFB_E_ARG; }
   if (n_bytes >= (1ull << 40)) { set_error("input too large"); return VCFB_E_ARG; }
@@ -334,10 +389,15 @@ int vcfb_deflate_dev(const uint8_t* src, size_t n_bytes, uint8_t* dst, size_t ds
   uint32_t* seg_size = reinterpret_cast<uint32_t*>(ws + p.sizes_off);
   unsigned long long* seg_off = reinterpret_cast<unsigned long long*>(ws + p.offs_off);
   uint8_t* regions = ws + p.regions_off;
+  uint16_t* tokens = reinterpret_cast<uint16_t*>(ws + p.tokens_off);
+  if (sample_bytes < 1 || sample_bytes > 16) { set_error("vcfb_deflate_rows_dev: sample_bytes must be in [1, 16]"); return VCFB_E_ARG; }
+  // rows too long for deflate's 32 KB window: runs and the previous sample only
+  const dfl::MatchParams mp = dfl::make_match_params((long long)row_bytes, sample_bytes);
   cudaError_t e;
   if (p.nseg) {
     note_kernel("deflate_segments");
-    deflate_segments_kernel<<<unsigned(p.nseg), NT, 0, s>>>(src, (long long)n_bytes, p.piece, regions, p.stride, seg_size);
+    deflate_segments_kernel<<<unsigned(p.nseg), NT, 0, s>>>(src, (long long)n_bytes, p.piece, mp, regions, p.stride, tokens,
+                                                          seg_size);
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "deflate_segments_kernel launch");
   }

@@ -50,10 +50,27 @@ def _as_device_bytes(x):
     return x
 
 
-def deflate_raw_dev(x):
+def row_geometry(x):
+    """``(row_bytes, sample_bytes)`` of an image-like array for the match candidates of the parse
+    (``vcfb_deflate_rows_dev``): for (..., H, W, C) the bytes of a row
+    and of a pixel, for (H, W) the bytes of a row and of a sample; ``(0, 1)`` (runs only) otherwise."""
+    shape = tuple(x.shape)
+    item = x.element_size() if _is_torch(x) else x.dtype.itemsize
+    if len(shape) == 2:
+        return shape[1] * item, item
+    if len(shape) >= 3:
+        return shape[-2] * shape[-1] * item, shape[-1] * item
+    return 0, 1
+
+
+def deflate_raw_dev(x, geometry=None):
     """Asynchronous on torch's current stream: returns ``(stream, n)`` -- a uint8 CUDA tensor of
-    capacity ``vcfb_deflate_bound`` and a one-element int64 CUDA tensor with the stream length."""
+    capacity ``vcfb_deflate_bound`` and a one-element int64 CUDA tensor with the stream length.
+    ``geometry``: ``(row_bytes, sample_bytes)``; by default from the shape of ``x``."""
     import torch
+    row_bytes, sample_bytes = geometry if geometry is not None else row_geometry(x)
+    if not 1 <= sample_bytes <= 16:
+        row_bytes, sample_bytes = 0, 1
     x = _as_device_bytes(x)
     L = _lib.lib()
     n = x.numel()
@@ -61,8 +78,8 @@ def deflate_raw_dev(x):
     ws = torch.empty(L.vcfb_deflate_workspace(n), dtype=torch.uint8, device=x.device)
     out_n = torch.zeros(1, dtype=torch.int64, device=x.device)
     with torch.cuda.device(x.device):
-        check(L.vcfb_deflate_dev(x.data_ptr(), n, dst.data_ptr(), dst.numel(), out_n.data_ptr(), ws.data_ptr(),
-                                 ws.numel(), torch.cuda.current_stream().cuda_stream))
+        check(L.vcfb_deflate_rows_dev(x.data_ptr(), n, row_bytes, sample_bytes, dst.data_ptr(), dst.numel(),
+                                      out_n.data_ptr(), ws.data_ptr(), ws.numel(), torch.cuda.current_stream().cuda_stream))
     return dst, out_n
 
 
@@ -108,9 +125,9 @@ def crc32_combine(crc1: int, crc2: int, len2: int) -> int:
     return _multmodp(p, crc1) ^ crc2
 
 
-def deflate_raw(x) -> bytes:
+def deflate_raw(x, geometry=None) -> bytes:
     """Raw deflate stream of the bytes of ``x`` (numpy array or torch tensor)."""
-    dst, out_n = deflate_raw_dev(x)
+    dst, out_n = deflate_raw_dev(x, geometry)
     n = int(out_n.item())
     return dst[:n].cpu().numpy().tobytes()
 
@@ -136,7 +153,7 @@ def zlib_compress(x) -> bytes:
     """zlib-format stream (what ``zlib.compress`` returns): ``zlib.decompress`` reads it.  Deflate
     stream and Adler-32 both come from the GPU; ``x``: numpy array or torch tensor."""
     dev = _as_device_bytes(x)
-    dst, out_n = deflate_raw_dev(dev)
+    dst, out_n = deflate_raw_dev(dev, row_geometry(x))
     ad = adler32_dev(dev)
     n = int(out_n.item())
     return b"\x78\x9c" + dst[:n].cpu().numpy().tobytes() + struct.pack(">I", int(ad.item()) & 0xFFFFFFFF)
@@ -239,7 +256,7 @@ def savez_compressed(file, **arrays) -> None:
             raise ValueError("object arrays are not supported")
         header = _npy_header(dtype, shape)
         dev = _as_device_bytes(src)                    # one upload (numpy) or none (CUDA tensor)
-        dst, out_n = deflate_raw_dev(dev)
+        dst, out_n = deflate_raw_dev(dev, row_geometry(src))
         crc_body = crc32_dev(dev)
         nbytes = int(out_n.item())
         members.append((name, header, dst[:nbytes].cpu().numpy().tobytes(), int(crc_body.item()) & 0xFFFFFFFF, dev.numel()))
