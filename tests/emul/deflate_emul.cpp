@@ -24,9 +24,11 @@ struct Store {                 // token j of a thread, laid out like the kernel'
 
 struct SampleAdd {
   uint32_t* cnt;
-  uint32_t* tot;               // [0] literals, [1] run starts
+  uint32_t* tot;               // [0] literals, [1] run starts, [2] words that are not a run, [3] of those found above
   void lit(int b) { ++cnt[b]; ++tot[0]; }
   void run() { ++tot[1]; }
+  void dense() { ++tot[2]; }
+  void hit() { ++tot[3]; }
 };
 }  // namespace
 
@@ -65,9 +67,10 @@ extern "C" long long dfl_emul(const uint8_t* src, long long n, int piece, int NT
     hist[dfl::EOB] = 1;
     dfl::CostModel cm;
     if (model) {
-      uint32_t cnt[256] = {0}, tot[2] = {0, 0};
+      uint32_t cnt[256] = {0}, tot[4] = {0, 0, 0, 0};
       SampleAdd add{cnt, tot};
-      for (int tid = 0; tid < NT; ++tid) dfl::sample_segment(src, n, s0, nseg, tid, NT, add);
+      for (int tid = 0; tid < NT; ++tid) dfl::sample_segment(src, n, s0, nseg, tid, NT, P, add);
+      cm.far_on = getenv("DFL_NOGATE") ? 1 : dfl::model_far_on(tot[2], tot[3]);
       for (int b = 0; b < 256; ++b) cm.lit8[b] = dfl::model_lit8(cnt, tot[0], tot[1], b);
       cm.len8 = dfl::model_len8(tot[0], tot[1]);
     }

@@ -134,6 +134,17 @@ DFL_HD uint64_t load_word(const uint8_t* src, long long n, long long base) {
   return x;
 }
 
+// the eight bytes at an arbitrary position (zeros past n); CHK = false: pos + 16 <= n
+template <bool CHK = true>
+DFL_HD uint64_t load_u64_at(const uint8_t* src, long long n, long long pos) {
+  const long long base = pos & ~7ll;
+  const int off = int(pos & 7);
+  const uint64_t w0 = load_word<CHK>(src, n, base);
+  if (!off) return w0;
+  const uint64_t w1 = (!CHK || base + 8 < n) ? load_word<CHK>(src, n, base + 8) : 0;
+  return (w0 >> (8 * off)) | (w1 << (64 - 8 * off));
+}
+
 // ---- cost model of the parse --------------------------------------------------------------------
 //
 // A greedy parse that takes every match it finds is larger than the run-length parse on dense planes:
@@ -165,6 +176,7 @@ DFL_HD int cost8_ratio(uint32_t num, uint32_t den) {
 struct CostModel {
   uint8_t lit8[256];    // estimated bits * 8 of a literal
   int len8;             // of a length symbol (without extra bits)
+  int far_on;           // whether the segment looks at the candidates other than the run at all
 };
 
 // Counts of one sampled word w at byte position pos: wp / wn are the words before and after it
@@ -191,15 +203,28 @@ DFL_HD void sample_word(uint64_t wp, uint64_t w, uint64_t wn, long long pos, lon
 }
 
 // the sampled words of the segment [s0, s0 + nseg) that thread tid of NT looks at
+// Also counted: the sampled words that are not one repeated byte (add.dense()) and those of them that
+// stand, all eight bytes, at one of the other candidate distances as well (add.hit()): where the
+// content is dense and almost none do -- noise, fine quantisation steps -- looking for such matches
+// costs more than half of the parse and finds nothing (model_far_on()).
 template <class Add>
-DFL_HD void sample_segment(const uint8_t* src, long long n, long long s0, long long nseg, int tid, int NT, Add& add) {
+DFL_HD void sample_segment(const uint8_t* src, long long n, long long s0, long long nseg, int tid, int NT,
+                           const MatchParams& P, Add& add) {
   const long long first = ((s0 + 7) / 8 + SAMPLE_EVERY - 1) / SAMPLE_EVERY * SAMPLE_EVERY;
   for (long long aw = first + (long long)SAMPLE_EVERY * tid; aw * 8 < s0 + nseg; aw += (long long)SAMPLE_EVERY * NT) {
     const long long pos = aw * 8;
-    sample_word(pos >= 8 ? load_word(src, n, pos - 8) : 0, load_word(src, n, pos), pos + 8 < n ? load_word(src, n, pos + 8) : 0,
-                pos, n, add);
+    const uint64_t w = load_word(src, n, pos);
+    sample_word(pos >= 8 ? load_word(src, n, pos - 8) : 0, w, pos + 8 < n ? load_word(src, n, pos + 8) : 0, pos, n, add);
+    if (P.nd > 1 && pos + 8 <= n && w != 0x0101010101010101ull * (w & 0xff)) {
+      add.dense();
+      for (int c = 1; c < P.nd; ++c)
+        if (pos >= P.dist[c] && load_u64_at(src, n, pos - P.dist[c]) == w) { add.hit(); break; }
+    }
   }
 }
+
+// dense, hits: the counts of sample_segment() over the segment
+DFL_HD int model_far_on(uint32_t dense, uint32_t hits) { return dense < 256 || hits * 16 >= dense; }
 
 // entry b of the cost table from the sampled counts (cnt[256] literals, nlit their sum, nrun run starts)
 DFL_HD uint8_t model_lit8(const uint32_t* cnt, uint32_t nlit, uint32_t nrun, int b) {
@@ -221,17 +246,6 @@ DFL_HD int model_len8(uint32_t nlit, uint32_t nrun) {
 
 
 // ---- parse ----------------------------------------------------------------------------------------
-
-// the eight bytes at an arbitrary position (zeros past n); CHK = false: pos + 16 <= n
-template <bool CHK = true>
-DFL_HD uint64_t load_u64_at(const uint8_t* src, long long n, long long pos) {
-  const long long base = pos & ~7ll;
-  const int off = int(pos & 7);
-  const uint64_t w0 = load_word<CHK>(src, n, base);
-  if (!off) return w0;
-  const uint64_t w1 = (!CHK || base + 8 < n) ? load_word<CHK>(src, n, base + 8) : 0;
-  return (w0 >> (8 * off)) | (w1 << (64 - 8 * off));
-}
 
 // number of bytes (at most lim) for which src[p + k] == src[p - d + k]; CHK = false: p + lim + 16 <= n
 template <bool CHK = true>
@@ -294,7 +308,7 @@ DFL_HD void parse_piece_impl(const uint8_t* src, long long n, long long s, long 
   int prev = p > 0 ? int(src[p - 1]) : -1;
   long long wbase = -8;
   uint64_t w = 0;
-  bool far_on = M && P.nd > 1;
+  bool far_on = M && P.nd > 1 && M->far_on;
   int fails = 0;
   while (p < e) {
     const long long base = p & ~7ll;

@@ -65,7 +65,7 @@ struct SegShared {
   uint32_t hist[288];
   uint32_t dhist[32];
   uint32_t scnt[256];     // sampled literals
-  uint32_t stot[2];       // their number, the number of sampled run starts
+  uint32_t stot[4];       // their number, the number of sampled run starts, of words that are not a run, of those found above
   dfl::MatchParams mp;
   dfl::CostModel cm;
   dfl::Codes codes;
@@ -83,6 +83,8 @@ struct SampleAdd {
   uint32_t* tot;
   __device__ void lit(int b) { atomicAdd(cnt + b, 1u); atomicAdd(tot, 1u); }
   __device__ void run() { atomicAdd(tot + 1, 1u); }
+  __device__ void dense() { atomicAdd(tot + 2, 1u); }
+  __device__ void hit() { atomicAdd(tot + 3, 1u); }
 };
 
 struct TokenStore {        // token j of this thread; the tokens of a segment are laid out j-major
@@ -110,23 +112,23 @@ deflate_segments_kernel(const uint8_t* __restrict__ src, long long n, int piece,
 
   uint16_t* tok = tokens + seg * seg_bytes + tid;
 
+  if (tid == 64) sh.mp = mp;
+  __syncthreads();
   for (int i = tid; i < 288; i += NT) sh.hist[i] = 0;
   if (tid < 256) sh.scnt[tid] = 0;
   if (tid < 32) sh.dhist[tid] = 0;
   if (tid <= dfl::MAX_LIT_BITS) sh.scratch.cnt[tid] = 0;
-  if (tid == 32) { sh.scratch.m = 0; sh.scratch.hi = 0; sh.stot[0] = 0; sh.stot[1] = 0; }
-  if (tid == 64) sh.mp = mp;
-  __syncthreads();
+  if (tid == 32) { sh.scratch.m = 0; sh.scratch.hi = 0; sh.stot[0] = 0; sh.stot[1] = 0; sh.stot[2] = 0; sh.stot[3] = 0; }
   if (tid == 0) sh.hist[dfl::EOB] = 1;
 
   // phase 0: cost model of the parse from a sample of the segment
   {
     SampleAdd add{sh.scnt, sh.stot};
-    dfl::sample_segment(src, n, s0, nseg, tid, NT, add);
+    dfl::sample_segment(src, n, s0, nseg, tid, NT, sh.mp, add);
   }
   __syncthreads();
   if (tid < 256) sh.cm.lit8[tid] = dfl::model_lit8(sh.scnt, sh.stot[0], sh.stot[1], tid);
-  if (tid == 256) sh.cm.len8 = dfl::model_len8(sh.stot[0], sh.stot[1]);
+  if (tid == 256) { sh.cm.len8 = dfl::model_len8(sh.stot[0], sh.stot[1]); sh.cm.far_on = dfl::model_far_on(sh.stot[2], sh.stot[3]); }
   __syncthreads();
 
   // phase 1: parse; tokens and their frequencies
