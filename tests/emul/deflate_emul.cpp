@@ -99,7 +99,13 @@ extern "C" long long dfl_emul(const uint8_t* src, long long n, int piece, int NT
     for (int tid = 0; tid < NT; ++tid) dfl::par_limit(scratch, dfl::MAX_LIT_BITS, tid);
     for (int tid = 0; tid < NT; ++tid) dfl::par_lengths(scratch, dfl::MAX_LIT_BITS, codes.len, tid, NT);
     for (int tid = 0; tid < NT; ++tid) dfl::par_codes(scratch, dfl::NLIT, codes.len, codes.code, tid, NT);
-    dfl::segment_header(scratch, codes, hdr);
+    for (int tid = 0; tid < NT; ++tid) dfl::hpar_prepare(codes, hdr, tid, NT);
+    for (int tid = NT - 1; tid >= 0; --tid) dfl::hpar_fill(codes, hdr, tid, NT);
+    for (int tid = 0; tid < NT; ++tid) dfl::hpar_count(hdr, tid, NT);
+    for (int tid = NT - 1; tid >= 0; --tid) dfl::hpar_tokens(hdr, tid, NT);
+    for (int tid = 0; tid < NT; ++tid) dfl::hpar_clcode(scratch, hdr, tid);
+    for (int tid = NT - 1; tid >= 0; --tid) dfl::hpar_size(hdr, tid, NT);
+    for (int tid = 0; tid < NT; ++tid) dfl::hpar_finish(hdr, tid);
     {
       // ... gives the code of the serial build_code()
       dfl::Codes c2 = codes;
@@ -111,6 +117,10 @@ extern "C" long long dfl_emul(const uint8_t* src, long long n, int piece, int NT
       dfl::segment_build(hist, s2, c2, h2);
       if (memcmp(c2.len, codes.len, sizeof c2.len) || memcmp(c2.code, codes.code, sizeof c2.code)) return -4;
       if (h2.bits != hdr.bits || h2.ntok != hdr.ntok || int(scratch.hi) != hi) return -5;
+      if (h2.hlit != hdr.hlit || h2.hdist != hdr.hdist || h2.hclen != hdr.hclen || memcmp(h2.tok_sym, hdr.tok_sym, size_t(h2.ntok)) ||
+          memcmp(h2.tok_ext, hdr.tok_ext, size_t(h2.ntok)) || memcmp(h2.cllen, hdr.cllen, sizeof h2.cllen) ||
+          memcmp(h2.clcode, hdr.clcode, sizeof h2.clcode))
+        return -7;
     }
     for (int tid = 0; tid < NT; ++tid) {
       dfl::SizeVisitor sv;

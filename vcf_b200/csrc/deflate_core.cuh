@@ -179,19 +179,32 @@ struct CostModel {
   int far_on;           // whether the segment looks at the candidates other than the run at all
 };
 
+// bit i: byte i of w equals byte i - 1 (byte -1 = pb).  Exact zero-byte detector on w ^ (w shifted by a byte).
+DFL_HD uint32_t eq_mask8(uint64_t w, uint32_t pb) {
+  const uint64_t x = w ^ ((w << 8) | uint64_t(pb & 0xff));
+  const uint64_t m7 = 0x7f7f7f7f7f7f7f7full;
+  const uint64_t z = ~(((x & m7) + m7) | x | m7);    // 0x80 where a byte of x is zero
+  return uint32_t(((z >> 7) * 0x0102040810204080ull) >> 56);
+}
+
 // Counts of one sampled word w at byte position pos: wp / wn are the words before and after it
 // (zero where there is none).  A byte belongs to a run when three consecutive bytes around it equal
 // their predecessors; every other byte counts as a literal, every start of a run as a match.
 template <class Add>
 DFL_HD void sample_word(uint64_t wp, uint64_t w, uint64_t wn, long long pos, long long n, Add& add) {
-  uint32_t eq = 0;                                   // bit i: byte i of (wp, w, wn) equals byte i - 1, i in [1, 24)
-  int prev = int(wp & 0xff);
-  for (int i = 1; i < 24; ++i) {
-    const uint64_t x = i < 8 ? wp : i < 16 ? w : wn;
-    const int b = int((x >> (8 * (i & 7))) & 0xff);
-    const long long at = pos - 8 + i;
-    if (b == prev && at >= 1 && at < n) eq |= 1u << i;
-    prev = b;
+  uint32_t eq;                                       // bit i: byte i of (wp, w, wn) equals byte i - 1, i in [1, 24)
+  if (pos >= 16 && pos + 16 <= n) {
+    eq = (eq_mask8(wp, 0) & 0xfeu) | (eq_mask8(w, uint32_t(wp >> 56)) << 8) | (eq_mask8(wn, uint32_t(w >> 56)) << 16);
+  } else {                                           // the ends of the input: positions outside [1, n) equal nothing
+    eq = 0;
+    int prev = int(wp & 0xff);
+    for (int i = 1; i < 24; ++i) {
+      const uint64_t x = i < 8 ? wp : i < 16 ? w : wn;
+      const int b = int((x >> (8 * (i & 7))) & 0xff);
+      const long long at = pos - 8 + i;
+      if (b == prev && at >= 1 && at < n) eq |= 1u << i;
+      prev = b;
+    }
   }
   const uint32_t t = eq & (eq >> 1) & (eq >> 2);     // bit i: bytes i, i + 1, i + 2 all equal their predecessors
   const uint32_t inrun = t | (t << 1) | (t << 2);
@@ -724,6 +737,10 @@ struct Header {
   uint16_t clcode[NCL];
   uint8_t cllen[NCL];
   int bits;                         // size of the whole header including BFINAL/BTYPE
+  // the CTA-parallel construction (hpar_*) only
+  uint8_t v[NLIT + NDIST + 4];      // the two length arrays one after the other
+  uint16_t tcnt[NLIT + NDIST + 4];  // tokens of the run that starts at i (0 elsewhere)
+  uint32_t tokbits;                 // sum of the tokens' sizes under the code-length code
 };
 
 DFL_HD void header_tok(Header& h, int sym, int ext) {
@@ -780,6 +797,120 @@ DFL_HD void header_finish(Header& h) {
     bits += h.cllen[s] + (s == 16 ? 2 : s == 17 ? 3 : s == 18 ? 7 : 0);
   }
   h.bits = bits;
+}
+
+// ---- the header in CTA-parallel steps ------------------------------------------------------------
+//
+// header_tokens() + header_finish() by one thread were ~10-20 % of a segment's time (every other
+// thread waits for the header's size before it can place its tokens).  The steps below are called by
+// all `nt` threads with their `tid`, a CTA barrier between consecutive steps; tokens, frequencies
+// and sizes equal the serial functions' (checked by the host emulation).
+
+DFL_HD void hpar_prepare(const Codes& c, Header& h, int tid, int nt) {
+  for (int i = tid; i < NCL; i += nt) h.clfreq[i] = 0;
+  if (tid != 0) return;
+  int hlit = NLIT;
+  while (hlit > 257 && c.len[hlit - 1] == 0) --hlit;
+  int hdist = NDIST;
+  while (hdist > 1 && c.dlen[hdist - 1] == 0) --hdist;
+  h.hlit = hlit;
+  h.hdist = hdist;
+  h.ntok = 0;
+  h.tokbits = 0;
+}
+
+DFL_HD void hpar_fill(const Codes& c, Header& h, int tid, int nt) {
+  const int total = h.hlit + h.hdist;
+  for (int i = tid; i < total; i += nt) h.v[i] = i < h.hlit ? c.len[i] : c.dlen[i - h.hlit];
+}
+
+// tokens of a run of r equal lengths v, in the order header_tokens() sends them; PUT(symbol, extra)
+template <class Put>
+DFL_HD int run_tokens(int v, int r, Put& put) {
+  int k = 0;
+  if (v == 0) {
+    while (r >= 11) { const int c = r < 138 ? r : 138; put(k++, 18, c - 11); r -= c; }
+    if (r >= 3) { put(k++, 17, r - 3); r = 0; }
+    while (r-- > 0) put(k++, 0, 0);
+  } else {
+    put(k++, v, 0);
+    --r;
+    while (r >= 3) { const int c = r < 6 ? r : 6; put(k++, 16, c - 3); r -= c; }
+    while (r-- > 0) put(k++, v, 0);
+  }
+  return k;
+}
+
+struct NoPut { DFL_HD void operator()(int, int, int) const {} };
+
+DFL_HD int run_length_at(const Header& h, int total, int i) {
+  const int v = h.v[i];
+  int r = 1;
+  while (i + r < total && h.v[i + r] == v) ++r;
+  return r;
+}
+
+DFL_HD void hpar_count(Header& h, int tid, int nt) {
+  const int total = h.hlit + h.hdist;
+  for (int i = tid; i < total; i += nt) {
+    int k = 0;
+    if (i == 0 || h.v[i] != h.v[i - 1]) {
+      NoPut np;
+      k = run_tokens(h.v[i], run_length_at(h, total, i), np);
+    }
+    h.tcnt[i] = uint16_t(k);
+  }
+}
+
+struct HeaderPut {
+  Header* h;
+  int base;
+  DFL_HD void operator()(int k, int sym, int ext) const {
+    h->tok_sym[base + k] = uint8_t(sym);
+    h->tok_ext[base + k] = uint8_t(ext);
+    DFL_ATOMIC_ADD(&h->clfreq[sym], 1u);
+  }
+};
+
+DFL_HD void hpar_tokens(Header& h, int tid, int nt) {
+  const int total = h.hlit + h.hdist;
+  for (int i = tid; i < total; i += nt) {
+    if (!h.tcnt[i]) continue;
+    int base = 0;
+    for (int j = 0; j < i; ++j) base += h.tcnt[j];
+    HeaderPut put{&h, base};
+    const int r = run_length_at(h, total, i);
+    const int k = run_tokens(h.v[i], r, put);
+    if (i + r == total) h.ntok = base + k;
+  }
+}
+
+// one thread: the code-length code from h.clfreq (S is free by now)
+DFL_HD void hpar_clcode(BuildScratch& S, Header& h, int tid) {
+  if (tid != 0) return;
+  int used = 0;
+  for (int i = 0; i < NCL; ++i) used += h.clfreq[i] != 0;
+  for (int i = 0; used < 2 && i < NCL; ++i)            // a complete code needs two symbols
+    if (h.clfreq[i] == 0) { h.clfreq[i] = 1; ++used; }
+  for (int i = 0; i < NCL; ++i)
+    if (h.clfreq[i]) S.sorted[rank_of(h.clfreq, NCL, i)] = uint16_t(i);
+  build_code(h.clfreq, NCL, used, MAX_CL_BITS, S, h.clcode, h.cllen);
+  int hclen = NCL;
+  while (hclen > 4 && h.cllen[cl_order(hclen - 1)] == 0) --hclen;
+  h.hclen = hclen;
+}
+
+DFL_HD void hpar_size(Header& h, int tid, int nt) {
+  uint32_t bits = 0;
+  for (int t = tid; t < h.ntok; t += nt) {
+    const int s = h.tok_sym[t];
+    bits += h.cllen[s] + (s == 16 ? 2 : s == 17 ? 3 : s == 18 ? 7 : 0);
+  }
+  if (bits) { DFL_ATOMIC_ADD(&h.tokbits, bits); }
+}
+
+DFL_HD void hpar_finish(Header& h, int tid) {
+  if (tid == 0) h.bits = 3 + 5 + 5 + 4 + 3 * h.hclen + int(h.tokbits);
 }
 
 DFL_HD void header_emit(const Header& h, BitWriter& bw) {

@@ -87,6 +87,21 @@ struct SampleAdd {
   __device__ void hit() { atomicAdd(tot + 3, 1u); }
 };
 
+// the kept tokens of a thread, four loads in flight
+template <class V>
+__device__ __forceinline__ void walk_tokens(const uint16_t* __restrict__ tok, int ntok, V& v) {
+  int j = 0;
+  for (; j + 4 <= ntok; j += 4) {
+    const uint16_t t0 = tok[(long long)j * NT], t1 = tok[(long long)(j + 1) * NT], t2 = tok[(long long)(j + 2) * NT],
+                   t3 = tok[(long long)(j + 3) * NT];
+    dfl::visit_token(t0, v);
+    dfl::visit_token(t1, v);
+    dfl::visit_token(t2, v);
+    dfl::visit_token(t3, v);
+  }
+  for (; j < ntok; ++j) dfl::visit_token(tok[(long long)j * NT], v);
+}
+
 struct TokenStore {        // token j of this thread; the tokens of a segment are laid out j-major
   uint16_t* base;
   __device__ void operator()(int j, uint16_t t) const { base[(long long)j * NT] = t; }
@@ -159,9 +174,18 @@ deflate_segments_kernel(const uint8_t* __restrict__ src, long long n, int piece,
   __syncthreads();
   dfl::par_codes(sh.scratch, dfl::NLIT, sh.codes.len, sh.codes.code, tid, NT);
   __syncthreads();
-  // the block header needs one thread and nothing below needs it before the scan: no barrier, the
-  // other warps size their pieces meanwhile
-  if (tid == 0) dfl::segment_header(sh.scratch, sh.codes, sh.hdr);
+  // the block header in CTA-parallel steps (run-length tokens of the two length arrays); its code-length
+  // code needs one thread and nothing below needs it before the sizes are summed: the other warps size
+  // their pieces meanwhile
+  dfl::hpar_prepare(sh.codes, sh.hdr, tid, NT);
+  __syncthreads();
+  dfl::hpar_fill(sh.codes, sh.hdr, tid, NT);
+  __syncthreads();
+  dfl::hpar_count(sh.hdr, tid, NT);
+  __syncthreads();
+  dfl::hpar_tokens(sh.hdr, tid, NT);
+  __syncthreads();
+  dfl::hpar_clcode(sh.scratch, sh.hdr, tid);
 
   // phase 3: sizes and bit offsets
   {
@@ -169,9 +193,11 @@ deflate_segments_kernel(const uint8_t* __restrict__ src, long long n, int piece,
     sv.c = &sh.codes;
     sv.P = &sh.mp;
     sv.bits = 0;
-    for (int j = 0; j < ntok; ++j) dfl::visit_token(tok[(long long)j * NT], sv);
+    walk_tokens(tok, ntok, sv);
     sh.off[tid] = sv.bits;
   }
+  __syncthreads();
+  dfl::hpar_size(sh.hdr, tid, NT);
   __syncthreads();
   {
     // exclusive scan of the pieces' bit counts (a segment stays below 2^32 bits): warp shuffles,
@@ -196,6 +222,7 @@ deflate_segments_kernel(const uint8_t* __restrict__ src, long long n, int piece,
       }
       if (lane < NT / 32) sh.wsum[lane] = wi - v;
       if (lane == 31) {
+        dfl::hpar_finish(sh.hdr, 0);
         const long long dyn = dfl::dynamic_size(sh.hdr, sh.codes, (long long)wi);
         const long long st = dfl::stored_size(nseg);
         sh.stored = dyn >= st;
@@ -227,7 +254,7 @@ deflate_segments_kernel(const uint8_t* __restrict__ src, long long n, int piece,
     ev.c = &sh.codes;
     ev.P = &sh.mp;
     ev.bw = &bw;
-    for (int j = 0; j < ntok; ++j) dfl::visit_token(tok[(long long)j * NT], ev);
+    walk_tokens(tok, ntok, ev);
     if (tid == NT - 1) dfl::segment_close(sh.codes, bw);
     bw.finish();
   }
