@@ -34,7 +34,8 @@ def timed(kb, geom, reps=10):
     return e0.elapsed_time(e1) / reps, int(nb.item()), dst
 
 
-for kind in ("natural", "noise"):
+KINDS = tuple(os.environ.get("KINDS", "natural,noise").split(","))
+for kind in KINDS:
     x = make_frames(torch, 16, H, W, dev, 99, kind)
     for q in (4, 8, 16, 32, 64):
         k = Codec(8, q).encode(x)

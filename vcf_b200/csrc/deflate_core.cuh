@@ -44,13 +44,20 @@ constexpr int FAR_MIN = 4;     // shortest match at a distance other than 1 (fou
 
 // ---- match lengths ------------------------------------------------------------------------------
 
+DFL_HD int ilog2_u32(uint32_t x) {           // x >= 1
+#if defined(__CUDA_ARCH__)
+  return 31 - __clz(int(x));
+#else
+  return 31 - __builtin_clz(x);
+#endif
+}
+
 // RFC 1951 3.2.5: length L in [3, 258] -> symbol 257..285, number of extra bits, extra value
 DFL_HD void length_symbol(int L, int* sym, int* ebits, int* eval) {
   if (L == MAX_MATCH) { *sym = 285; *ebits = 0; *eval = 0; return; }
   const int l = L - 3;
   if (l < 8) { *sym = 257 + l; *ebits = 0; *eval = 0; return; }
-  int e = 0;                       // floor(log2(l)) - 2, l in [8, 254] -> e in [1, 5]
-  for (int t = l >> 3; t; t >>= 1) ++e;
+  const int e = ilog2_u32(uint32_t(l)) - 2;    // l in [8, 254] -> e in [1, 5]
   *sym = 261 + 4 * e + ((l >> e) & 3);
   *ebits = e;
   *eval = l & ((1 << e) - 1);
@@ -126,8 +133,10 @@ inline MatchParams make_match_params(long long row, int pixel) {
 // src must be 8-byte aligned.  The input is read as aligned 64-bit words; bytes past n are never touched.
 // CHK = false: the caller knows that base + 8 <= n (every piece but the last few of the input), which
 // takes a 64-bit comparison and a branch off every load -- a sixth of the parse's instructions.
-template <bool CHK = true>
-DFL_HD uint64_t load_word(const uint8_t* src, long long n, long long base) {
+// I: the type positions are held in -- long long, or int where the caller has moved src close to them
+// (32-bit arithmetic: half the instructions of the 64-bit one on this machine).
+template <bool CHK = true, class I = long long>
+DFL_HD uint64_t load_word(const uint8_t* src, long long n, I base) {
   if (!CHK || base + 8 <= n) return *reinterpret_cast<const uint64_t*>(src + base);
   uint64_t x = 0;
   for (int k = 0; base + k < n; ++k) x |= uint64_t(src[base + k]) << (8 * k);
@@ -135,9 +144,9 @@ DFL_HD uint64_t load_word(const uint8_t* src, long long n, long long base) {
 }
 
 // the eight bytes at an arbitrary position (zeros past n); CHK = false: pos + 16 <= n
-template <bool CHK = true>
-DFL_HD uint64_t load_u64_at(const uint8_t* src, long long n, long long pos) {
-  const long long base = pos & ~7ll;
+template <bool CHK = true, class I = long long>
+DFL_HD uint64_t load_u64_at(const uint8_t* src, long long n, I pos) {
+  const I base = pos & ~I(7);
   const int off = int(pos & 7);
   const uint64_t w0 = load_word<CHK>(src, n, base);
   if (!off) return w0;
@@ -155,14 +164,6 @@ DFL_HD uint64_t load_u64_at(const uint8_t* src, long long n, long long pos) {
 // tokens) decide whether a match is worth its bits.
 
 constexpr int SAMPLE_EVERY = 4;
-
-DFL_HD int ilog2_u32(uint32_t x) {           // x >= 1
-#if defined(__CUDA_ARCH__)
-  return 31 - __clz(int(x));
-#else
-  return 31 - __builtin_clz(x);
-#endif
-}
 
 // 8 * log2(num / den), num >= den >= 1, num < 2^23
 DFL_HD int cost8_ratio(uint32_t num, uint32_t den) {
@@ -261,8 +262,8 @@ DFL_HD int model_len8(uint32_t nlit, uint32_t nrun) {
 // ---- parse ----------------------------------------------------------------------------------------
 
 // number of bytes (at most lim) for which src[p + k] == src[p - d + k]; CHK = false: p + lim + 16 <= n
-template <bool CHK = true>
-DFL_HD int match_length(const uint8_t* src, long long n, long long p, int d, int lim) {
+template <bool CHK = true, class I = long long>
+DFL_HD int match_length(const uint8_t* src, long long n, I p, int d, int lim) {
   int L = 0;
   while (L < lim) {
     const uint64_t x = load_u64_at<CHK>(src, n, p + L) ^ load_u64_at<CHK>(src, n, p + L - d);
@@ -285,25 +286,30 @@ DFL_HD int run_cost8(int r, int lit8, const MatchParams& P, const CostModel& M) 
 // estimated size of src[p, p + L) under the run-length parse (prev = the byte before p): what a
 // match at another distance has to beat.  Eight bytes at a time where they continue a run; gives
 // up (returning what it has) once the estimate is above `enough`.
-template <bool CHK = true>
-DFL_HD int span_cost8(const uint8_t* src, long long n, long long p, int L, int prev, const MatchParams& P,
+template <bool CHK = true, class I = long long>
+DFL_HD int span_cost8(const uint8_t* src, long long n, I p, int L, int prev, const MatchParams& P,
                       const CostModel& M, int enough) {
-  int cost = 0, run = 0, pb = prev;
-  for (int k = 0; k < L;) {
+  int cost = 0, last = -1, cur = prev;                  // last: the latest byte that differs from its predecessor
+  uint32_t pb = uint32_t(prev);
+  for (int k = 0; k < L; k += 8) {
     const uint64_t w = load_u64_at<CHK>(src, n, p + k);
     const int nb = L - k < 8 ? L - k : 8;
-    if (nb == 8 && pb >= 0 && w == 0x0101010101010101ull * uint64_t(pb)) { run += 8; k += 8; continue; }
-    for (int i = 0; i < nb; ++i) {
-      const int b = int((w >> (8 * i)) & 0xff);
-      if (b == pb) { ++run; continue; }
-      if (run) { cost += run_cost8(run, int(M.lit8[pb]), P, M); run = 0; }
-      cost += M.lit8[b];
-      pb = b;
+    uint32_t m = ~eq_mask8(w, pb) & ((1u << nb) - 1u);
+    if (prev < 0 && k == 0) m |= 1u;                    // the first byte of the input has no predecessor
+    while (m) {
+      const int i = DFL_CTZ64(uint64_t(m));
+      m &= m - 1;
+      const int run = k + i - last - 1;
+      if (run) cost += run_cost8(run, int(M.lit8[cur & 0xff]), P, M);
+      cur = int((w >> (8 * i)) & 0xff);
+      cost += M.lit8[cur];
+      last = k + i;
     }
-    k += nb;
     if (cost > enough) return cost;
+    pb = uint32_t(w >> 56);
   }
-  if (run) cost += run_cost8(run, int(M.lit8[pb]), P, M);
+  const int run = L - last - 1;
+  if (run) cost += run_cost8(run, int(M.lit8[cur & 0xff]), P, M);
   return cost;
 }
 
@@ -314,26 +320,27 @@ DFL_HD int span_cost8(const uint8_t* src, long long n, long long p, int L, int p
 // decoder has produced it by then).  V::lit(byte) / V::match(length, candidate).  M == nullptr:
 // every run of MIN_MATCH bytes or more is a match (the plain run-length parse; one candidate only).
 // CHK = false: e + 16 <= n, no load looks at n.
-template <bool CHK, class V>
-DFL_HD void parse_piece_impl(const uint8_t* src, long long n, long long s, long long e, const MatchParams& P,
-                        const CostModel* M, V& v) {
-  long long p = s;
-  int prev = p > 0 ? int(src[p - 1]) : -1;
-  long long wbase = -8;
+// `lowest`: the position of the first byte of the input (0 unless src has been moved).
+template <bool CHK, class I, class V>
+DFL_HD void parse_piece_impl(const uint8_t* src, long long n, I s, I e, I lowest, const MatchParams& P,
+                             const CostModel* M, V& v) {
+  I p = s;
+  int prev = p > lowest ? int(src[p - 1]) : -1;
+  I wbase = (s & ~I(7)) - 8;
   uint64_t w = 0;
   bool far_on = M && P.nd > 1 && M->far_on;
   int fails = 0;
   while (p < e) {
-    const long long base = p & ~7ll;
+    const I base = p & ~I(7);
     if (base != wbase) { w = load_word<CHK>(src, n, base); wbase = base; }
     const int b = int((w >> (8 * int(p & 7))) & 0xff);
-    const long long rem = e - p;
+    const I rem = e - p;
     const int lim = rem < MAX_MATCH ? int(rem) : MAX_MATCH;
     int best = 0, bc = 0;
     if (b == prev) {
       const uint64_t splat = 0x0101010101010101ull * uint64_t(prev);
       int L = 0;
-      long long rb = wbase;
+      I rb = wbase;
       uint64_t rw = w;
       for (;;) {
         const int off = int((p + L) & 7);
@@ -360,7 +367,7 @@ DFL_HD void parse_piece_impl(const uint8_t* src, long long n, long long s, long 
       int fl = 0, fc = 0;                                  // the longest match at another distance
       for (int c = 1; c < P.nd; ++c) {
         const int d = P.dist[c];
-        if (p < d) continue;
+        if (p - d < lowest) continue;
         const uint64_t x = win ^ load_u64_at<CHK>(src, n, p - d);
         int L = x ? (DFL_CTZ64(x) >> 3) : 8;
         if (L < FAR_MIN) continue;
@@ -393,8 +400,13 @@ DFL_HD void parse_piece_impl(const uint8_t* src, long long n, long long s, long 
 template <class V>
 DFL_HD void parse_piece(const uint8_t* src, long long n, long long s, long long e, const MatchParams& P,
                         const CostModel* M, V& v) {
-  if (e + 16 <= n) parse_piece_impl<false>(src, n, s, e, P, M, v);
-  else parse_piece_impl<true>(src, n, s, e, P, M, v);
+  if (e + 16 <= n) {            // all but the last pieces of the input: no bound checks, positions relative to the piece
+    const long long s8 = s & ~7ll;
+    const int lowest = s8 > (1ll << 30) ? -(1 << 30) : -int(s8);
+    parse_piece_impl<false, int>(src + s8, n, int(s - s8), int(e - s8), lowest, P, M, v);
+  } else {
+    parse_piece_impl<true, long long>(src, n, s, e, 0ll, P, M, v);
+  }
 }
 
 // A token in 16 bits: a literal is its byte; a match is 256 + (length - 3) in bits 0..8 and the
