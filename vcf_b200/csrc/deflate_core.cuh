@@ -149,6 +149,8 @@ DFL_HD uint64_t load_u64_at(const uint8_t* src, long long n, I pos) {
   const I base = pos & ~I(7);
   const int off = int(pos & 7);
   const uint64_t w0 = load_word<CHK>(src, n, base);
+  if (!CHK)                       // both words without a branch: independent loads stay in flight together
+    return (w0 >> (8 * off)) | ((load_word<false>(src, n, base + 8) << 1) << (63 - 8 * off));
   if (!off) return w0;
   const uint64_t w1 = (!CHK || base + 8 < n) ? load_word<CHK>(src, n, base + 8) : 0;
   return (w0 >> (8 * off)) | (w1 << (64 - 8 * off));
@@ -321,7 +323,9 @@ DFL_HD int span_cost8(const uint8_t* src, long long n, I p, int L, int prev, con
 // every run of MIN_MATCH bytes or more is a match (the plain run-length parse; one candidate only).
 // CHK = false: e + 16 <= n, no load looks at n.
 // `lowest`: the position of the first byte of the input (0 unless src has been moved).
-template <bool CHK, class I, class V>
+// NC > 0: exactly NC candidates besides the run -- their first eight bytes are fetched and compared without a
+// branch in between, so the loads are in flight together (the walk is latency-bound); NC = -1: any number.
+template <bool CHK, class I, int NC, class V>
 DFL_HD void parse_piece_impl(const uint8_t* src, long long n, I s, I e, I lowest, const MatchParams& P,
                              const CostModel* M, V& v) {
   I p = s;
@@ -365,15 +369,35 @@ DFL_HD void parse_piece_impl(const uint8_t* src, long long n, I s, I e, I lowest
     if (far_on && best < lim && best < P.good && lim >= FAR_MIN) {
       const uint64_t win = load_u64_at<CHK>(src, n, p);
       int fl = 0, fc = 0;                                  // the longest match at another distance
-      for (int c = 1; c < P.nd; ++c) {
-        const int d = P.dist[c];
-        if (p - d < lowest) continue;
-        const uint64_t x = win ^ load_u64_at<CHK>(src, n, p - d);
-        int L = x ? (DFL_CTZ64(x) >> 3) : 8;
-        if (L < FAR_MIN) continue;
-        if (L == 8 && lim > 8) L += match_length<CHK>(src, n, p + 8, d, lim - 8);
-        if (L > lim) L = lim;
-        if (L > fl) { fl = L; fc = c; }
+      if constexpr (NC > 0) {
+        int first[NC];
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+          const int d = P.dist[k + 1];
+          const bool ok = p - d >= lowest;
+          const uint64_t x = win ^ load_u64_at<CHK>(src, n, ok ? I(p - d) : p);
+          const int L = x ? (DFL_CTZ64(x) >> 3) : 8;
+          first[k] = ok ? L : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < NC; ++k) {
+          int L = first[k];
+          if (L < FAR_MIN) continue;
+          if (L == 8 && lim > 8) L += match_length<CHK>(src, n, I(p + 8), P.dist[k + 1], lim - 8);
+          if (L > lim) L = lim;
+          if (L > fl) { fl = L; fc = k + 1; }
+        }
+      } else {
+        for (int c = 1; c < P.nd; ++c) {
+          const int d = P.dist[c];
+          if (p - d < lowest) continue;
+          const uint64_t x = win ^ load_u64_at<CHK>(src, n, I(p - d));
+          int L = x ? (DFL_CTZ64(x) >> 3) : 8;
+          if (L < FAR_MIN) continue;
+          if (L == 8 && lim > 8) L += match_length<CHK>(src, n, I(p + 8), d, lim - 8);
+          if (L > lim) L = lim;
+          if (L > fl) { fl = L; fc = c; }
+        }
       }
       bool taken = false;
       if (fl > best) {
@@ -403,9 +427,10 @@ DFL_HD void parse_piece(const uint8_t* src, long long n, long long s, long long 
   if (e + 16 <= n) {            // all but the last pieces of the input: no bound checks, positions relative to the piece
     const long long s8 = s & ~7ll;
     const int lowest = s8 > (1ll << 30) ? -(1 << 30) : -int(s8);
-    parse_piece_impl<false, int>(src + s8, n, int(s - s8), int(e - s8), lowest, P, M, v);
+    if (P.nd == 5) parse_piece_impl<false, int, 4>(src + s8, n, int(s - s8), int(e - s8), lowest, P, M, v);    // make_match_params() of an image
+    else parse_piece_impl<false, int, -1>(src + s8, n, int(s - s8), int(e - s8), lowest, P, M, v);
   } else {
-    parse_piece_impl<true, long long>(src, n, s, e, 0ll, P, M, v);
+    parse_piece_impl<true, long long, -1>(src, n, s, e, 0ll, P, M, v);
   }
 }
 

@@ -25,6 +25,7 @@
 #include <stdlib.h>
 
 namespace vcfb {
+namespace fast { int sm_count(); }      // kernels_fast.cu
 namespace {
 
 constexpr int NT = 512;
@@ -107,11 +108,10 @@ struct TokenStore {        // token j of this thread; the tokens of a segment ar
   __device__ void operator()(int j, uint16_t t) const { base[(long long)j * NT] = t; }
 };
 
-#ifndef DFL_MINB
-#define DFL_MINB 3
-#endif
-
-__global__ void __launch_bounds__(NT, DFL_MINB)
+// MINB = 3 (40 registers, some spills): the most segments in flight, for batches; MINB = 2 (64 registers, no
+// spills): faster per segment, for inputs that do not fill the GPU anyway (one 4K frame is 189 segments).
+template <int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 deflate_segments_kernel(const uint8_t* __restrict__ src, long long n, int piece, dfl::MatchParams mp,
                         uint8_t* __restrict__ regions, long long stride, uint16_t* __restrict__ tokens,
                         uint32_t* __restrict__ seg_size) {
@@ -425,8 +425,12 @@ int vcfb_deflate_rows_dev(const uint8_t* src, size_t n_bytes, size_t row_bytes, 
   cudaError_t e;
   if (p.nseg) {
     note_kernel("deflate_segments");
-    deflate_segments_kernel<<<unsigned(p.nseg), NT, 0, s>>>(src, (long long)n_bytes, p.piece, mp, regions, p.stride, tokens,
-                                                          seg_size);
+    if (p.nseg <= 2ll * fast::sm_count())
+      deflate_segments_kernel<2><<<unsigned(p.nseg), NT, 0, s>>>(src, (long long)n_bytes, p.piece, mp, regions, p.stride,
+                                                                 tokens, seg_size);
+    else
+      deflate_segments_kernel<3><<<unsigned(p.nseg), NT, 0, s>>>(src, (long long)n_bytes, p.piece, mp, regions, p.stride,
+                                                                 tokens, seg_size);
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "deflate_segments_kernel launch");
   }
