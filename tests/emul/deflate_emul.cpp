@@ -86,8 +86,18 @@ extern "C" long long dfl_emul(const uint8_t* src, long long n, int piece, int NT
       if (tv.n > piece) return -6;
     }
     {
+      // the kernel's steps ...
       dfl::BuildScratch sd;
-      dfl::distance_code(dhist, sd, codes);
+      uint32_t dh2[32];
+      memcpy(dh2, dhist, sizeof dh2);
+      for (int tid = 0; tid < NT; ++tid) dfl::dpar_prepare(dhist, sd, tid);
+      for (int tid = NT - 1; tid >= 0; --tid) dfl::dpar_rank(dhist, sd, tid, NT);
+      for (int tid = 0; tid < NT; ++tid) dfl::dpar_build(dhist, sd, codes, tid);
+      // ... give the code of the one-thread function
+      dfl::Codes cd;
+      dfl::BuildScratch sd2;
+      dfl::distance_code(dh2, sd2, cd);
+      if (memcmp(cd.dlen, codes.dlen, dfl::NDIST) || memcmp(cd.dcode, codes.dcode, dfl::NDIST * sizeof(uint16_t))) return -8;
     }
     // the kernel's CTA-parallel construction, one step after the other ...
     scratch.m = 0;
@@ -102,7 +112,10 @@ extern "C" long long dfl_emul(const uint8_t* src, long long n, int piece, int NT
     for (int tid = 0; tid < NT; ++tid) dfl::hpar_prepare(codes, hdr, tid, NT);
     for (int tid = NT - 1; tid >= 0; --tid) dfl::hpar_fill(codes, hdr, tid, NT);
     for (int tid = 0; tid < NT; ++tid) dfl::hpar_count(hdr, tid, NT);
+    for (int tid = NT - 1; tid >= 0; --tid) dfl::hpar_blocks(hdr, tid, NT);
     for (int tid = NT - 1; tid >= 0; --tid) dfl::hpar_tokens(hdr, tid, NT);
+    for (int tid = 0; tid < NT; ++tid) dfl::hpar_clprepare(hdr, tid);
+    for (int tid = NT - 1; tid >= 0; --tid) dfl::hpar_clrank(scratch, hdr, tid, NT);
     for (int tid = 0; tid < NT; ++tid) dfl::hpar_clcode(scratch, hdr, tid);
     for (int tid = NT - 1; tid >= 0; --tid) dfl::hpar_size(hdr, tid, NT);
     for (int tid = 0; tid < NT; ++tid) dfl::hpar_finish(hdr, tid);

@@ -777,6 +777,9 @@ struct Header {
   // the CTA-parallel construction (hpar_*) only
   uint8_t v[NLIT + NDIST + 4];      // the two length arrays one after the other
   uint16_t tcnt[NLIT + NDIST + 4];  // tokens of the run that starts at i (0 elsewhere)
+  uint16_t rlen[NLIT + NDIST + 4];  // its length
+  uint16_t bsum[(NLIT + NDIST + 4) / 16 + 1];   // tokens per 16 positions
+  int clused;                       // code-length symbols in use
   uint32_t tokbits;                 // sum of the tokens' sizes under the code-length code
 };
 
@@ -890,12 +893,23 @@ DFL_HD int run_length_at(const Header& h, int total, int i) {
 DFL_HD void hpar_count(Header& h, int tid, int nt) {
   const int total = h.hlit + h.hdist;
   for (int i = tid; i < total; i += nt) {
-    int k = 0;
+    int k = 0, r = 0;
     if (i == 0 || h.v[i] != h.v[i - 1]) {
       NoPut np;
-      k = run_tokens(h.v[i], run_length_at(h, total, i), np);
+      r = run_length_at(h, total, i);
+      k = run_tokens(h.v[i], r, np);
     }
     h.tcnt[i] = uint16_t(k);
+    h.rlen[i] = uint16_t(r);
+  }
+}
+
+DFL_HD void hpar_blocks(Header& h, int tid, int nt) {
+  const int total = h.hlit + h.hdist;
+  for (int b = tid; b * 16 < total; b += nt) {
+    int sum = 0;
+    for (int i = b * 16; i < b * 16 + 16 && i < total; ++i) sum += h.tcnt[i];
+    h.bsum[b] = uint16_t(sum);
   }
 }
 
@@ -914,24 +928,34 @@ DFL_HD void hpar_tokens(Header& h, int tid, int nt) {
   for (int i = tid; i < total; i += nt) {
     if (!h.tcnt[i]) continue;
     int base = 0;
-    for (int j = 0; j < i; ++j) base += h.tcnt[j];
+    for (int b = 0; b < (i >> 4); ++b) base += h.bsum[b];
+    for (int j = i & ~15; j < i; ++j) base += h.tcnt[j];
     HeaderPut put{&h, base};
-    const int r = run_length_at(h, total, i);
+    const int r = h.rlen[i];
     const int k = run_tokens(h.v[i], r, put);
     if (i + r == total) h.ntok = base + k;
   }
 }
 
-// one thread: the code-length code from h.clfreq (S is free by now)
-DFL_HD void hpar_clcode(BuildScratch& S, Header& h, int tid) {
+// the code-length code from h.clfreq (S is free by now): a complete code needs two symbols (one thread),
+// ranks by all threads, construction by one thread
+DFL_HD void hpar_clprepare(Header& h, int tid) {
   if (tid != 0) return;
   int used = 0;
   for (int i = 0; i < NCL; ++i) used += h.clfreq[i] != 0;
-  for (int i = 0; used < 2 && i < NCL; ++i)            // a complete code needs two symbols
+  for (int i = 0; used < 2 && i < NCL; ++i)
     if (h.clfreq[i] == 0) { h.clfreq[i] = 1; ++used; }
-  for (int i = 0; i < NCL; ++i)
+  h.clused = used;
+}
+
+DFL_HD void hpar_clrank(BuildScratch& S, Header& h, int tid, int nt) {
+  for (int i = tid; i < NCL; i += nt)
     if (h.clfreq[i]) S.sorted[rank_of(h.clfreq, NCL, i)] = uint16_t(i);
-  build_code(h.clfreq, NCL, used, MAX_CL_BITS, S, h.clcode, h.cllen);
+}
+
+DFL_HD void hpar_clcode(BuildScratch& S, Header& h, int tid) {
+  if (tid != 0) return;
+  build_code(h.clfreq, NCL, h.clused, MAX_CL_BITS, S, h.clcode, h.cllen);
   int hclen = NCL;
   while (hclen > 4 && h.cllen[cl_order(hclen - 1)] == 0) --hclen;
   h.hclen = hclen;
@@ -999,6 +1023,36 @@ DFL_HD void distance_code(uint32_t* dhist, BuildScratch& S, Codes& c) {
   for (int i = 0; i < NDIST; ++i)
     if (dhist[i]) S.sorted[rank_of(dhist, NDIST, i)] = uint16_t(i);
   build_code(dhist, NDIST, used, MAX_LIT_BITS, S, c.dcode, c.dlen);
+}
+
+// The same in steps for the kernel (one thread / all threads / one thread, a CTA barrier between them; they
+// run beside par_rank, par_tree and par_count): the 900 comparisons of the ranks by one thread were a tenth
+// of a segment's time.  S.m carries the number of symbols in use.
+DFL_HD void dpar_prepare(uint32_t* dhist, BuildScratch& S, int tid) {
+  if (tid != 0) return;
+  int used = 0;
+  for (int i = 0; i < NDIST; ++i) used += dhist[i] != 0;
+  for (int i = 0; used < 2 && i < NDIST; ++i)
+    if (dhist[i] == 0) { dhist[i] = 1; ++used; }
+  S.m = uint32_t(used);
+}
+
+DFL_HD void dpar_rank(const uint32_t* dhist, BuildScratch& S, int tid, int nt) {
+  for (int i = tid; i < NDIST; i += nt)
+    if (dhist[i]) S.sorted[rank_of(dhist, NDIST, i)] = uint16_t(i);
+}
+
+DFL_HD void dpar_build(const uint32_t* dhist, BuildScratch& S, Codes& c, int tid) {
+  if (tid != 0) return;
+  if (S.m == 2) {                        // runs only: two codes of one bit, the lower symbol gets 0
+    int k = 0;
+    for (int i = 0; i < NDIST; ++i) {
+      c.dlen[i] = dhist[i] ? 1 : 0;
+      c.dcode[i] = dhist[i] ? uint16_t(k++) : uint16_t(0);
+    }
+    return;
+  }
+  build_code(dhist, NDIST, int(S.m), MAX_LIT_BITS, S, c.dcode, c.dlen);
 }
 
 // hist: frequencies of the literal/length symbols of the segment (EOB counted once, so at least

@@ -158,14 +158,16 @@ deflate_segments_kernel(const uint8_t* __restrict__ src, long long n, int piece,
     ntok = tv.n;
   }
   __syncthreads();
-  if (tid == 32) dfl::distance_code(sh.dhist, sh.dscratch, sh.codes);     // a few symbols: one thread, beside the rank sort
-
   // phase 2: code construction
-  //  (the steps of deflate_core.cuh: only the two-queue merge, the Kraft fix and the header are serial)
+  //  (the steps of deflate_core.cuh: only the two-queue merge and the Kraft fix are serial; the distance code
+  //  -- a few symbols -- is built by warps 1 and 2 beside the first three steps)
+  dfl::dpar_prepare(sh.dhist, sh.dscratch, tid - 32);
   dfl::par_rank(sh.hist, dfl::NLIT, sh.scratch, sh.codes.code, sh.codes.len, tid, NT);
   __syncthreads();
+  if (tid >= 64 && tid < 96) dfl::dpar_rank(sh.dhist, sh.dscratch, tid - 64, 32);
   dfl::par_tree(sh.scratch, tid);
   __syncthreads();
+  dfl::dpar_build(sh.dhist, sh.dscratch, sh.codes, tid - 32);
   dfl::par_count(sh.scratch, dfl::MAX_LIT_BITS, tid, NT);
   __syncthreads();
   dfl::par_limit(sh.scratch, dfl::MAX_LIT_BITS, tid);
@@ -174,16 +176,22 @@ deflate_segments_kernel(const uint8_t* __restrict__ src, long long n, int piece,
   __syncthreads();
   dfl::par_codes(sh.scratch, dfl::NLIT, sh.codes.len, sh.codes.code, tid, NT);
   __syncthreads();
-  // the block header in CTA-parallel steps (run-length tokens of the two length arrays); its code-length
-  // code needs one thread and nothing below needs it before the sizes are summed: the other warps size
-  // their pieces meanwhile
+  // the block header in CTA-parallel steps (run-length tokens of the two length arrays, ranks of the
+  // code-length symbols); the construction of the code-length code needs one thread and nothing below needs it
+  // before the sizes are summed: the other warps size their pieces meanwhile
   dfl::hpar_prepare(sh.codes, sh.hdr, tid, NT);
   __syncthreads();
   dfl::hpar_fill(sh.codes, sh.hdr, tid, NT);
   __syncthreads();
   dfl::hpar_count(sh.hdr, tid, NT);
   __syncthreads();
+  dfl::hpar_blocks(sh.hdr, tid, NT);
+  __syncthreads();
   dfl::hpar_tokens(sh.hdr, tid, NT);
+  __syncthreads();
+  dfl::hpar_clprepare(sh.hdr, tid);
+  __syncthreads();
+  dfl::hpar_clrank(sh.scratch, sh.hdr, tid, NT);
   __syncthreads();
   dfl::hpar_clcode(sh.scratch, sh.hdr, tid);
 
