@@ -39,12 +39,9 @@ extern "C" long long dfl_emul(const uint8_t* src, long long n, int piece, int NT
   dfl::MatchParams P = dfl::make_match_params(row, pixel);
   if (nd > 0) {
     P.nd = 1;
-    for (int i = 1; i < nd; ++i) dfl::match_params_add(P, dists[i], dfl::FAR_MIN);
+    for (int i = 1; i < nd; ++i) dfl::match_params_add(P, dists[i]);
   }
   if (!model) P.nd = 1;
-  if (const char* e = getenv("DFL_MARGIN8")) P.margin8 = atoi(e);
-  if (const char* e = getenv("DFL_PATIENCE")) P.patience = atoi(e);
-  if (const char* e = getenv("DFL_DCOST")) for (int i = 1; i < P.nd; ++i) P.dcost8[i] = uint8_t(P.dcost8[i] + atoi(e));
   std::vector<uint16_t> tokens((size_t)NT * piece);
   std::vector<int> ntok(NT);
   const long long seg_bytes = (long long)NT * piece;
@@ -70,7 +67,7 @@ extern "C" long long dfl_emul(const uint8_t* src, long long n, int piece, int NT
       uint32_t cnt[256] = {0}, tot[4] = {0, 0, 0, 0};
       SampleAdd add{cnt, tot};
       for (int tid = 0; tid < NT; ++tid) dfl::sample_segment(src, n, s0, nseg, tid, NT, P, add);
-      cm.far_on = getenv("DFL_NOGATE") ? 1 : dfl::model_far_on(tot[2], tot[3]);
+      cm.far_on = dfl::model_far_on(tot[2], tot[3]);
       for (int b = 0; b < 256; ++b) cm.lit8[b] = dfl::model_lit8(cnt, tot[0], tot[1], b);
       cm.len8 = dfl::model_len8(tot[0], tot[1]);
     }

@@ -80,23 +80,20 @@ DFL_HD void distance_symbol(int d, int* sym, int* ebits, int* eval) {
 struct MatchParams {
   int nd;
   int good;                     // a run at least this long is taken without looking at the other candidates
-  int margin8;                  // estimated saving (1/8 bit) a match at another distance must exceed
   int patience;                 // positions in a row without such a match after which a piece stops looking for one
   int dist[MAX_CAND];
   uint8_t dsym[MAX_CAND], debits[MAX_CAND];
   uint16_t deval[MAX_CAND];
-  uint8_t minlen[MAX_CAND];     // shortest match at this distance
   uint8_t dcost8[MAX_CAND];     // estimated size of the distance code + its extra bits, in 1/8 bit
 };
 
-inline void match_params_add(MatchParams& P, int d, int minlen) {
+inline void match_params_add(MatchParams& P, int d) {
   if (d < 1 || d > 32768 || P.nd >= MAX_CAND) return;
   for (int i = 0; i < P.nd; ++i) if (P.dist[i] == d) return;
   int s, eb, ev;
   distance_symbol(d, &s, &eb, &ev);
   const int i = P.nd++;
   P.dist[i] = d; P.dsym[i] = uint8_t(s); P.debits[i] = uint8_t(eb); P.deval[i] = uint16_t(ev);
-  P.minlen[i] = uint8_t(minlen);
   P.dcost8[i] = uint8_t(d == 1 ? 12 : 8 * (3 + eb));     // the run distance gets the shortest code; the others about 3 bits
 }
 
@@ -108,17 +105,16 @@ inline MatchParams make_match_params(long long row, int pixel) {
   MatchParams P;
   P.nd = 0;
   P.good = 64;
-  P.margin8 = 0;
   P.patience = 64;
-  for (int i = 0; i < MAX_CAND; ++i) { P.dist[i] = 0; P.dsym[i] = 0; P.debits[i] = 0; P.deval[i] = 0; P.minlen[i] = 0; P.dcost8[i] = 0; }
-  match_params_add(P, 1, MIN_MATCH);
+  for (int i = 0; i < MAX_CAND; ++i) { P.dist[i] = 0; P.dsym[i] = 0; P.debits[i] = 0; P.deval[i] = 0; P.dcost8[i] = 0; }
+  match_params_add(P, 1);
   if (pixel < 1) pixel = 1;
   if (row > 0) {
-    if (pixel > 1) match_params_add(P, pixel, FAR_MIN);
+    if (pixel > 1) match_params_add(P, pixel);
     if (row > 2 * pixel && row + pixel <= 32768) {
-      match_params_add(P, int(row), FAR_MIN);
-      match_params_add(P, int(row) - pixel, FAR_MIN);
-      match_params_add(P, int(row) + pixel, FAR_MIN);
+      match_params_add(P, int(row));
+      match_params_add(P, int(row) - pixel);
+      match_params_add(P, int(row) + pixel);
     }
   }
   return P;
@@ -403,7 +399,7 @@ DFL_HD void parse_piece_impl(const uint8_t* src, long long n, I s, I e, I lowest
       if (fl > best) {
         int sym, eb, ev;
         length_symbol(fl, &sym, &eb, &ev);
-        const int cost = M->len8 + 8 * eb + int(P.dcost8[fc]) + P.margin8;
+        const int cost = M->len8 + 8 * eb + int(P.dcost8[fc]);
         if (span_cost8<CHK>(src, n, p, fl, prev, P, *M, cost) > cost) { best = fl; bc = fc; taken = true; }
       }
       if (taken) fails = 0;
