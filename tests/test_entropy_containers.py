@@ -63,6 +63,21 @@ def test_tiff_container_is_read_by_libtiff_and_pillow():
             assert np.array_equal(np.array(Image.open(io.BytesIO(t))).reshape(a.shape), a)
 
 
+def test_row_geometry_of_the_arrays_the_entropy_stage_gets():
+    """Bytes per row and per sample handed to vcfb_deflate_rows_dev: the H x W x 3 uint8 index image of
+    src/2D-DCT.py:361-364, 16-bit images (src/TIFF.py:26), batches, planes, flat arrays."""
+    from vcf_b200.entropy import row_geometry
+    assert row_geometry(np.zeros((4, 10, 3), np.uint8)) == (30, 3)
+    assert row_geometry(np.zeros((4, 10, 3), np.uint16)) == (60, 6)
+    assert row_geometry(np.zeros((2, 4, 10, 3), np.uint8)) == (30, 3)
+    assert row_geometry(np.zeros((4, 10), np.uint8)) == (10, 1)
+    assert row_geometry(np.zeros((4, 10), np.int16)) == (20, 2)
+    assert row_geometry(np.zeros(40, np.uint8)) == (0, 1)
+    import torch
+    assert row_geometry(torch.zeros((4, 10, 3), dtype=torch.uint8)) == (30, 3)
+    assert row_geometry(torch.zeros((4, 10), dtype=torch.int16)) == (20, 2)
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():

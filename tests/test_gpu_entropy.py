@@ -183,6 +183,15 @@ def test_argument_errors():
     big = torch.zeros(L.vcfb_deflate_bound(1000), dtype=torch.uint8, device="cuda")
     with pytest.raises(VcfbError):
         _lib.check(L.vcfb_deflate_dev(x.data_ptr(), 1000, big.data_ptr(), big.numel(), n.data_ptr(), ws.data_ptr(), 8, None))
+    for bad_sample in (0, -1, 17):
+        with pytest.raises(VcfbError):
+            _lib.check(L.vcfb_deflate_rows_dev(x.data_ptr(), 1000, 100, bad_sample, big.data_ptr(), big.numel(), n.data_ptr(),
+                                               ws.data_ptr(), ws.numel(), None))
+    # a row beyond deflate's window is not an error: the candidates above are dropped
+    _lib.check(L.vcfb_deflate_rows_dev(x.data_ptr(), 1000, 1 << 20, 3, big.data_ptr(), big.numel(), n.data_ptr(), ws.data_ptr(),
+                                       ws.numel(), None))
+    torch.cuda.synchronize()
+    assert zlib.decompress(big[: int(n.item())].cpu().numpy().tobytes(), -15) == bytes(1000)
 
 
 def test_crc32_equals_zlib():
