@@ -39,6 +39,7 @@ extern "C" long long dfl_emul(const uint8_t* src, long long n, int piece, int NT
   dfl::MatchParams P = dfl::make_match_params(row, pixel);
   if (nd > 0) {
     P.nd = 1;
+    P.rows3 = 0;
     for (int i = 1; i < nd; ++i) dfl::match_params_add(P, dists[i]);
   }
   if (!model) P.nd = 1;

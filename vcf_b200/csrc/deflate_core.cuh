@@ -81,6 +81,7 @@ struct MatchParams {
   int nd;
   int good;                     // a run at least this long is taken without looking at the other candidates
   int patience;                 // positions in a row without such a match after which a piece stops looking for one
+  int rows3;                    // the candidates are 1, px, row, row - px, row + px with px in [2, 4] (and row > 2 px)
   int dist[MAX_CAND];
   uint8_t dsym[MAX_CAND], debits[MAX_CAND];
   uint16_t deval[MAX_CAND];
@@ -106,6 +107,7 @@ inline MatchParams make_match_params(long long row, int pixel) {
   P.nd = 0;
   P.good = 64;
   P.patience = 64;
+  P.rows3 = 0;
   for (int i = 0; i < MAX_CAND; ++i) { P.dist[i] = 0; P.dsym[i] = 0; P.debits[i] = 0; P.deval[i] = 0; P.dcost8[i] = 0; }
   match_params_add(P, 1);
   if (pixel < 1) pixel = 1;
@@ -115,6 +117,7 @@ inline MatchParams make_match_params(long long row, int pixel) {
       match_params_add(P, int(row));
       match_params_add(P, int(row) - pixel);
       match_params_add(P, int(row) + pixel);
+      P.rows3 = P.nd == 5 && pixel >= 2 && pixel <= 4;
     }
   }
   return P;
@@ -259,6 +262,13 @@ DFL_HD int model_len8(uint32_t nlit, uint32_t nrun) {
 
 // ---- parse ----------------------------------------------------------------------------------------
 
+// the eight bytes at byte offset off (0 <= off <= 15) of three consecutive words
+DFL_HD uint64_t window3(uint64_t w0, uint64_t w1, uint64_t w2, int off) {
+  const uint64_t lo = off >= 8 ? w1 : w0, hi = off >= 8 ? w2 : w1;
+  const int sh = 8 * (off & 7);
+  return (lo >> sh) | ((hi << 1) << (63 - sh));
+}
+
 // number of bytes (at most lim) for which src[p + k] == src[p - d + k]; CHK = false: p + lim + 16 <= n
 template <bool CHK = true, class I = long long>
 DFL_HD int match_length(const uint8_t* src, long long n, I p, int d, int lim) {
@@ -367,13 +377,37 @@ DFL_HD void parse_piece_impl(const uint8_t* src, long long n, I s, I e, I lowest
       int fl = 0, fc = 0;                                  // the longest match at another distance
       if constexpr (NC > 0) {
         int first[NC];
+        bool done = false;
+        if constexpr (NC == 4) {
+          // make_match_params() of an image with samples of 2-4 bytes: the three positions above lie within 24
+          // bytes of each other -- three aligned words serve all of them (five loads per position instead of eight)
+          const int px = P.dist[1];
+          const I top = p - P.dist[4];                     // the lowest of them: row + px back
+          if (top >= lowest) {
+            const I wb = top & ~I(7);
+            const int o = int(top & 7);
+            const uint64_t w0 = load_word<CHK>(src, n, wb), w1 = load_word<CHK>(src, n, I(wb + 8)),
+                           w2 = load_word<CHK>(src, n, I(wb + 16));
+            const uint64_t x1 = win ^ load_u64_at<CHK>(src, n, I(p - px));
+            const uint64_t x4 = win ^ window3(w0, w1, w2, o);
+            const uint64_t x2 = win ^ window3(w0, w1, w2, o + px);
+            const uint64_t x3 = win ^ window3(w0, w1, w2, o + 2 * px);
+            first[0] = x1 ? (DFL_CTZ64(x1) >> 3) : 8;
+            first[1] = x2 ? (DFL_CTZ64(x2) >> 3) : 8;
+            first[2] = x3 ? (DFL_CTZ64(x3) >> 3) : 8;
+            first[3] = x4 ? (DFL_CTZ64(x4) >> 3) : 8;
+            done = true;
+          }
+        }
+        if (!done) {
 #pragma unroll
-        for (int k = 0; k < NC; ++k) {
-          const int d = P.dist[k + 1];
-          const bool ok = p - d >= lowest;
-          const uint64_t x = win ^ load_u64_at<CHK>(src, n, ok ? I(p - d) : p);
-          const int L = x ? (DFL_CTZ64(x) >> 3) : 8;
-          first[k] = ok ? L : 0;
+          for (int k = 0; k < NC; ++k) {
+            const int d = P.dist[k + 1];
+            const bool ok = p - d >= lowest;
+            const uint64_t x = win ^ load_u64_at<CHK>(src, n, ok ? I(p - d) : p);
+            const int L = x ? (DFL_CTZ64(x) >> 3) : 8;
+            first[k] = ok ? L : 0;
+          }
         }
 #pragma unroll
         for (int k = 0; k < NC; ++k) {
@@ -423,7 +457,7 @@ DFL_HD void parse_piece(const uint8_t* src, long long n, long long s, long long 
   if (e + 16 <= n) {            // all but the last pieces of the input: no bound checks, positions relative to the piece
     const long long s8 = s & ~7ll;
     const int lowest = s8 > (1ll << 30) ? -(1 << 30) : -int(s8);
-    if (P.nd == 5) parse_piece_impl<false, int, 4>(src + s8, n, int(s - s8), int(e - s8), lowest, P, M, v);    // make_match_params() of an image
+    if (P.rows3) parse_piece_impl<false, int, 4>(src + s8, n, int(s - s8), int(e - s8), lowest, P, M, v);    // make_match_params() of an image
     else parse_piece_impl<false, int, -1>(src + s8, n, int(s - s8), int(e - s8), lowest, P, M, v);
   } else {
     parse_piece_impl<true, long long, -1>(src, n, s, e, 0ll, P, M, v);
